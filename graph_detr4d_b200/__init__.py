@@ -1,0 +1,13 @@
+"""graph_detr4d_b200 -- B200-native (sm_100a) cross-view 3D->2D feature-sampling
+attention for Graph-DETR4D, behind the reference's mmcv ATTENTION module API.
+
+(The directory is ``graph_detr4d_b200`` rather than ``graph-detr4d_b200`` because
+a hyphen cannot appear in a Python package name.)
+"""
+from . import _lib, ops, synthetic  # noqa: F401
+from .modules import (ATTENTION, Deform3DCrossAttn, Detr3DCrossAtten, build_attention,  # noqa: F401
+                      clear_caches, inverse_sigmoid)
+from .ops import (MODE_A, MODE_C, PackedFeatures, XViewConfig, pack_features,  # noqa: F401
+                  xview_attention, xview_backward, xview_forward)
+
+__version__ = "0.1.0"

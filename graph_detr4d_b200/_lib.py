@@ -1,0 +1,117 @@
+"""ctypes binding of libgd4d_xview.so (the C ABI in include/gd4d_xview.h).
+
+There is deliberately NO fallback: if the shared library is missing or was not
+built for this GPU, every op raises.  ``load()`` builds in-tree with nvcc when the
+library is absent (the build box has nvcc but no GPU; the GPU box receives the
+prebuilt .so with the repo snapshot).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import _build
+
+ABI_VERSION = 1
+MAX_LEVELS = 8
+MODE_A, MODE_C, MODE_V2 = 0, 1, 2
+F32, BF16 = 0, 1
+
+EXPORTS = (
+    "gd4d_abi_version",
+    "gd4d_strerror",
+    "gd4d_xview_launch_info",
+    "gd4d_xview_forward",
+    "gd4d_xview_backward",
+    "gd4d_pack_nchw",
+)
+
+
+class XViewParams(C.Structure):
+    """Mirror of ``gd4d_xview_params`` (include/gd4d_xview.h) -- keep in sync."""
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("mode", C.c_int32),
+        ("value_dtype", C.c_int32),
+        ("B", C.c_int32), ("Q", C.c_int32), ("N", C.c_int32), ("Hh", C.c_int32),
+        ("L", C.c_int32), ("P", C.c_int32), ("C", C.c_int32),
+        ("level_h", C.c_int32 * MAX_LEVELS),
+        ("level_w", C.c_int32 * MAX_LEVELS),
+        ("pc_lo", C.c_float * 3),
+        ("pc_span", C.c_float * 3),
+        ("img_h", C.c_float), ("img_w", C.c_float),
+        ("value", C.c_void_p * MAX_LEVELS),
+        ("value_bias", C.c_void_p),
+        ("ref", C.c_void_p),
+        ("lidar2img", C.c_void_p),
+        ("attn_logits", C.c_void_p),
+        ("offsets", C.c_void_p),
+        ("cam_logits", C.c_void_p),
+        ("out", C.c_void_p),
+        ("mask", C.c_void_p),
+        ("grad_out", C.c_void_p),
+        ("grad_value", C.c_void_p * MAX_LEVELS),
+        ("grad_value_bias", C.c_void_p),
+        ("grad_attn_logits", C.c_void_p),
+        ("grad_offsets", C.c_void_p),
+        ("grad_cam_logits", C.c_void_p),
+        ("grad_ref", C.c_void_p),
+    ]
+
+
+class Gd4dError(RuntimeError):
+    def __init__(self, status: int, what: str):
+        self.status = status
+        super().__init__(f"{what}: gd4d status {status} ({strerror(status)})")
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if needed) and type the C-ABI library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+            _build.build()
+        lib = C.CDLL(path)
+        lib.gd4d_abi_version.restype = C.c_int
+        lib.gd4d_abi_version.argtypes = []
+        lib.gd4d_strerror.restype = C.c_char_p
+        lib.gd4d_strerror.argtypes = [C.c_int]
+        lib.gd4d_xview_launch_info.restype = C.c_int
+        lib.gd4d_xview_launch_info.argtypes = [C.POINTER(XViewParams), C.POINTER(C.c_int32),
+                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.gd4d_xview_forward.restype = C.c_int
+        lib.gd4d_xview_forward.argtypes = [C.POINTER(XViewParams), C.c_void_p]
+        lib.gd4d_xview_backward.restype = C.c_int
+        lib.gd4d_xview_backward.argtypes = [C.POINTER(XViewParams), C.c_void_p]
+        lib.gd4d_pack_nchw.restype = C.c_int
+        lib.gd4d_pack_nchw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        if lib.gd4d_abi_version() != ABI_VERSION:
+            raise RuntimeError("libgd4d_xview.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def strerror(status: int) -> str:
+    return load().gd4d_strerror(int(status)).decode()
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise Gd4dError(status, what)

@@ -1,0 +1,110 @@
+// extern "C" boundary: validation, launch geometry, dispatch.  No allocation, no
+// synchronisation, stream-ordered, re-entrant (include/gd4d_xview.h).
+#include "xview_common.cuh"
+
+namespace gd4d {
+int dispatch_forward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
+int dispatch_backward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
+int dispatch_pack(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t images, int C,
+                  int H, int W, cudaStream_t stream);
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int validate(const gd4d_xview_params* p, bool backward, LaunchGeom* g) {
+  if (p == nullptr) return GD4D_ERR_NULL;
+  if (p->abi_version != GD4D_ABI_VERSION) return GD4D_ERR_UNSUPPORTED;
+  if (p->mode != GD4D_MODE_A && p->mode != GD4D_MODE_C) return GD4D_ERR_UNSUPPORTED;
+  if (p->value_dtype != GD4D_F32 && p->value_dtype != GD4D_BF16) return GD4D_ERR_UNSUPPORTED;
+  if (p->B <= 0 || p->Q <= 0 || p->N <= 0 || p->Hh <= 0 || p->L <= 0 || p->P <= 0 || p->C <= 0)
+    return GD4D_ERR_DIMS;
+  if (p->L > GD4D_MAX_LEVELS || p->P > 255 || p->N >= (1 << 22)) return GD4D_ERR_DIMS;
+  if (p->C % p->Hh != 0) return GD4D_ERR_DIMS;
+  if (p->C / p->Hh != kHeadDim) return GD4D_ERR_HEAD_DIM;
+  if (!(p->img_h > 0.f) || !(p->img_w > 0.f)) return GD4D_ERR_DIMS;
+  for (int l = 0; l < p->L; ++l) {
+    if (p->level_h[l] <= 0 || p->level_w[l] <= 0) return GD4D_ERR_DIMS;
+    if (p->value[l] == nullptr) return GD4D_ERR_NULL;
+    if (!aligned16(p->value[l])) return GD4D_ERR_ALIGN;
+    if (backward && p->grad_value[l] != nullptr && !aligned16(p->grad_value[l])) return GD4D_ERR_ALIGN;
+  }
+  if (p->ref == nullptr || p->lidar2img == nullptr || p->attn_logits == nullptr) return GD4D_ERR_NULL;
+  if (p->mode == GD4D_MODE_C) {
+    if (p->offsets == nullptr || p->cam_logits == nullptr) return GD4D_ERR_NULL;
+    if (p->L * p->P > kMaxLP) return GD4D_ERR_UNSUPPORTED;
+  }
+  if (backward) {
+    if (p->grad_out == nullptr) return GD4D_ERR_NULL;
+    if (!aligned16(p->grad_out)) return GD4D_ERR_ALIGN;
+  } else {
+    if (p->out == nullptr) return GD4D_ERR_NULL;
+    if (!aligned16(p->out)) return GD4D_ERR_ALIGN;
+  }
+  const long long warps = static_cast<long long>(p->B) * p->Q * p->Hh;
+  const long long ctas = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (ctas > 0x7fffffffLL) return GD4D_ERR_DIMS;
+  const int pp = p->mode == GD4D_MODE_C ? p->P : 1;
+  const long long cand_cap = static_cast<long long>(p->N) * pp;
+  // backward keeps 16 more bytes per candidate (coordinate-gradient accumulators)
+  const long long per_cand = backward ? 32 : 16;
+  const long long per_warp = sizeof(float) * kMaxLP * (backward ? 5 : 1) + per_cand * cand_cap;
+  const long long smem = per_warp * kWarpsPerCta;
+  if (smem > 200 * 1024) return GD4D_ERR_UNSUPPORTED;
+  g->grid = static_cast<int>(ctas);
+  g->block = kWarpsPerCta * 32;
+  g->smem = static_cast<int>(smem);
+  g->cand_cap = static_cast<int>(cand_cap);
+  return GD4D_OK;
+}
+}  // namespace gd4d
+
+extern "C" {
+
+int gd4d_abi_version(void) { return GD4D_ABI_VERSION; }
+
+const char* gd4d_strerror(int status) {
+  switch (status) {
+    case GD4D_OK: return "ok";
+    case GD4D_ERR_NULL: return "required pointer is NULL";
+    case GD4D_ERR_DIMS: return "bad or inconsistent dimension";
+    case GD4D_ERR_HEAD_DIM: return "unsupported head width (C/Hh must be 32)";
+    case GD4D_ERR_ALIGN: return "pointer not 16-byte aligned";
+    case GD4D_ERR_UNSUPPORTED: return "unsupported mode / dtype / size";
+    case GD4D_ERR_CUDA: return "CUDA launch failed";
+    default: return "unknown gd4d status";
+  }
+}
+
+int gd4d_xview_launch_info(const gd4d_xview_params* p, int32_t* grid, int32_t* block,
+                           int32_t* smem_bytes) {
+  gd4d::LaunchGeom g{};
+  const int st = gd4d::validate(p, false, &g);
+  if (st != GD4D_OK) return st;
+  if (grid) *grid = g.grid;
+  if (block) *block = g.block;
+  if (smem_bytes) *smem_bytes = g.smem;
+  return GD4D_OK;
+}
+
+int gd4d_xview_forward(const gd4d_xview_params* p, void* cuda_stream) {
+  gd4d::LaunchGeom g{};
+  const int st = gd4d::validate(p, false, &g);
+  if (st != GD4D_OK) return st;
+  return gd4d::dispatch_forward(*p, g, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int gd4d_xview_backward(const gd4d_xview_params* p, void* cuda_stream) {
+  gd4d::LaunchGeom g{};
+  const int st = gd4d::validate(p, true, &g);
+  if (st != GD4D_OK) return st;
+  return gd4d::dispatch_backward(*p, g, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int gd4d_pack_nchw(const void* src, void* dst, int32_t src_dtype, int32_t dst_dtype, int64_t images,
+                   int32_t C, int32_t H, int32_t W, void* cuda_stream) {
+  if (src == nullptr || dst == nullptr) return GD4D_ERR_NULL;
+  if (images <= 0 || C <= 0 || H <= 0 || W <= 0) return GD4D_ERR_DIMS;
+  return gd4d::dispatch_pack(src, dst, src_dtype, dst_dtype, images, C, H, W,
+                             static_cast<cudaStream_t>(cuda_stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+"""Host side of the cross-view sampling ops: torch tensors in, C-ABI calls out.
+
+PyTorch is plumbing here (device memory, the current CUDA stream, autograd
+bookkeeping); all arithmetic of the path runs in libgd4d_xview.so.  There is no
+CPU / eager fallback: CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, MODE_A, MODE_C, MODE_V2, XViewParams
+
+__all__ = ["XViewConfig", "pack_features", "PackedFeatures", "xview_forward", "xview_backward",
+           "xview_attention", "lidar2img_to_tensor", "MODE_A", "MODE_C", "MODE_V2"]
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"feature maps must be float32 or bfloat16, got {t.dtype}")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the cross-view sampling path has no CPU "
+                           f"fallback (the CPU oracle lives in oracle/ and is test-only)")
+
+
+def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    _require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# feature packing (NCHW -> channel-last), once per forward, shared by the 6 layers
+# --------------------------------------------------------------------------------------
+class _PackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat: torch.Tensor, out_dtype: torch.dtype):
+        B, N, Cc, H, W = feat.shape
+        src = feat.contiguous()
+        dst = torch.empty((B * N, H, W, Cc), device=feat.device, dtype=out_dtype)
+        st = _lib.load().gd4d_pack_nchw(src.data_ptr(), dst.data_ptr(), _dtype_code(src),
+                                        _dtype_code(dst), B * N, Cc, H, W, _stream_ptr(feat.device))
+        _lib.check(st, "gd4d_pack_nchw")
+        ctx.shape = (B, N, Cc, H, W)
+        ctx.in_dtype = feat.dtype
+        return dst
+
+    @staticmethod
+    def backward(ctx, grad):
+        B, N, Cc, H, W = ctx.shape
+        # (B*N,H,W,C) -> a (B,N,C,H,W) VIEW with channels-last strides: no copy
+        g = grad.permute(0, 3, 1, 2).unflatten(0, (B, N))
+        if g.dtype != ctx.in_dtype:
+            g = g.to(ctx.in_dtype)
+        return g, None
+
+
+def pack_level(feat: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """(B,N,C,H,W) -> channel-last (B*N,H,W,C).  Zero-copy when the map already is
+    channels_last in memory (a backbone run in torch.channels_last hands us that)."""
+    _require_cuda(feat, "feature map")
+    if feat.dim() != 5:
+        raise ValueError(f"feature map must be (B,N,C,H,W), got {tuple(feat.shape)}")
+    dtype = dtype or feat.dtype
+    B, N, Cc, H, W = feat.shape
+    if dtype == feat.dtype:
+        try:
+            nhwc = feat.view(B * N, Cc, H, W).permute(0, 2, 3, 1)
+        except RuntimeError:
+            nhwc = None
+        if nhwc is not None and nhwc.is_contiguous():
+            return nhwc  # already channel-last in memory
+    return _PackFn.apply(feat, dtype)
+
+
+@dataclass
+class PackedFeatures:
+    """Channel-last feature maps of one forward, plus the batch/camera split."""
+    levels: List[torch.Tensor]            # each (B*N, H_l, W_l, C)
+    B: int
+    N: int
+
+    @property
+    def C(self) -> int:
+        return self.levels[0].shape[-1]
+
+    @property
+    def shapes(self) -> List[Tuple[int, int]]:
+        return [(int(v.shape[1]), int(v.shape[2])) for v in self.levels]
+
+
+def pack_features(mlvl_feats: Sequence[torch.Tensor], dtype: Optional[torch.dtype] = None) -> PackedFeatures:
+    """Pack the reference's ``value`` (python list of (B,N,C,H,W) maps,
+    detr3d_transformer.py:142-143) once; all decoder layers then share it."""
+    B, N = int(mlvl_feats[0].shape[0]), int(mlvl_feats[0].shape[1])
+    return PackedFeatures([pack_level(f, dtype) for f in mlvl_feats], B, N)
+
+
+def lidar2img_to_tensor(img_metas, device) -> torch.Tensor:
+    """img_metas[b]['lidar2img'] (list of N np(4,4), float64 or float32) -> (B,N,4,4)
+    fp32 on the device; float64->float32 rounding as reference_points.new_tensor
+    does it (detr3d_transformer.py:398-402)."""
+    arr = np.asarray([m["lidar2img"] for m in img_metas])
+    return torch.as_tensor(arr.astype(np.float32)).to(device, non_blocking=True)
+
+
+# --------------------------------------------------------------------------------------
+# raw C-ABI calls
+# --------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class XViewConfig:
+    mode: int
+    num_heads: int
+    num_points: int
+    pc_range: Tuple[float, ...]
+    img_h: float
+    img_w: float
+
+
+def _fill_params(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
+                 offsets, cam_logits, lidar2img) -> XViewParams:
+    L = len(values)
+    if L > _lib.MAX_LEVELS:
+        raise ValueError(f"at most {_lib.MAX_LEVELS} feature levels")
+    Cc = int(values[0].shape[-1])
+    p = XViewParams()
+    p.abi_version = _lib.ABI_VERSION
+    p.mode = cfg.mode
+    p.value_dtype = _dtype_code(values[0])
+    p.B, p.Q, p.N = B, int(ref.shape[1]), N
+    p.Hh = cfg.num_heads if cfg.mode != MODE_A else Cc // 32
+    p.L, p.P, p.C = L, cfg.num_points, Cc
+    for l, v in enumerate(values):
+        if v.dim() != 4 or v.shape[0] != B * N or v.shape[-1] != Cc or not v.is_contiguous():
+            raise ValueError("value levels must be contiguous channel-last (B*N,H,W,C)")
+        if v.dtype != values[0].dtype or v.device != values[0].device:
+            raise ValueError("all value levels must share dtype and device")
+        p.level_h[l], p.level_w[l] = int(v.shape[1]), int(v.shape[2])
+        p.value[l] = v.data_ptr()
+    pc = cfg.pc_range
+    for i in range(3):
+        p.pc_lo[i] = float(pc[i])
+        p.pc_span[i] = float(pc[3 + i] - pc[i])      # python double subtraction, then fp32
+    p.img_h, p.img_w = float(cfg.img_h), float(cfg.img_w)
+    p.ref = ref.data_ptr()
+    p.lidar2img = lidar2img.data_ptr()
+    p.attn_logits = attn_logits.data_ptr()
+    p.offsets = offsets.data_ptr() if offsets is not None else None
+    p.cam_logits = cam_logits.data_ptr() if cam_logits is not None else None
+    return p
+
+
+def _check_shapes(cfg, B, N, L, Cc, ref, attn_logits, offsets, cam_logits, lidar2img):
+    Q = ref.shape[1]
+    if tuple(ref.shape) != (B, Q, 3):
+        raise ValueError(f"reference_points must be (B,Q,3), got {tuple(ref.shape)}")
+    if tuple(lidar2img.shape) != (B, N, 4, 4):
+        raise ValueError(f"lidar2img must be (B,N,4,4)=({B},{N},4,4), got {tuple(lidar2img.shape)}")
+    P = cfg.num_points
+    if cfg.mode == MODE_A:
+        want = B * Q * N * P * L
+    else:
+        want = B * Q * cfg.num_heads * L * P
+        if offsets is None or offsets.numel() != B * Q * cfg.num_heads * P * 3:
+            raise ValueError("offsets must hold B*Q*Hh*P*3 values")
+        if cam_logits is None or cam_logits.numel() != B * Q * N:
+            raise ValueError("cam_logits must hold B*Q*N values")
+    if attn_logits.numel() != want:
+        raise ValueError(f"attn_logits holds {attn_logits.numel()} values, expected {want}")
+
+
+def xview_forward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
+                  offsets=None, cam_logits=None, lidar2img=None, want_mask: bool = False):
+    """One fused forward launch.  Returns (out (B,Q,C) fp32, mask uint8 or None)."""
+    for v in values:
+        _require_cuda(v, "value")
+    ref = _f32c(ref, "reference_points")
+    attn_logits = _f32c(attn_logits, "attn_logits")
+    offsets = _f32c(offsets, "offsets")
+    cam_logits = _f32c(cam_logits, "cam_logits")
+    lidar2img = _f32c(lidar2img, "lidar2img")
+    L, Cc = len(values), int(values[0].shape[-1])
+    _check_shapes(cfg, B, N, L, Cc, ref, attn_logits, offsets, cam_logits, lidar2img)
+    p = _fill_params(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, lidar2img)
+    Q = int(ref.shape[1])
+    out = torch.empty((B, Q, Cc), device=ref.device, dtype=torch.float32)
+    p.out = out.data_ptr()
+    mask = None
+    if want_mask:
+        shape = (B, Q, N) if cfg.mode != MODE_C else (B, N, Q, cfg.num_heads, cfg.num_points)
+        mask = torch.zeros(shape, device=ref.device, dtype=torch.uint8)
+        p.mask = mask.data_ptr()
+    st = _lib.load().gd4d_xview_forward(C.byref(p), _stream_ptr(ref.device))
+    _lib.check(st, "gd4d_xview_forward")
+    return out, mask
+
+
+def xview_backward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
+                   offsets, cam_logits, lidar2img, grad_out, grad_values: Optional[Sequence[torch.Tensor]],
+                   need_ref: bool = True, need_offsets: bool = True):
+    """One fused backward launch.  ``grad_values`` (fp32 channel-last, same shapes as
+    ``values``) are ACCUMULATED into; the small gradients are returned fresh."""
+    grad_out = _f32c(grad_out, "grad_out")
+    p = _fill_params(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, lidar2img)
+    p.grad_out = grad_out.data_ptr()
+    if grad_values is not None:
+        for l, gvl in enumerate(grad_values):
+            if gvl.dtype != torch.float32 or gvl.shape != values[l].shape or not gvl.is_contiguous():
+                raise ValueError("grad_values must be fp32, contiguous, shaped like the value levels")
+            p.grad_value[l] = gvl.data_ptr()
+    # one zero-fill for all small gradients
+    n_attn = attn_logits.numel()
+    n_off = offsets.numel() if (offsets is not None and need_offsets) else 0
+    n_cam = cam_logits.numel() if cam_logits is not None else 0
+    n_ref = ref.numel() if need_ref else 0
+    small = torch.zeros(n_attn + n_off + n_cam + n_ref, device=ref.device, dtype=torch.float32)
+    g_attn = small[:n_attn].view(attn_logits.shape)
+    o = n_attn
+    g_off = small[o:o + n_off].view(offsets.shape) if n_off else None
+    o += n_off
+    g_cam = small[o:o + n_cam].view(cam_logits.shape) if n_cam else None
+    o += n_cam
+    g_ref = small[o:o + n_ref].view(ref.shape) if n_ref else None
+    p.grad_attn_logits = g_attn.data_ptr()
+    p.grad_offsets = g_off.data_ptr() if g_off is not None else None
+    p.grad_cam_logits = g_cam.data_ptr() if g_cam is not None else None
+    p.grad_ref = g_ref.data_ptr() if g_ref is not None else None
+    st = _lib.load().gd4d_xview_backward(C.byref(p), _stream_ptr(ref.device))
+    _lib.check(st, "gd4d_xview_backward")
+    return g_attn, g_off, g_cam, g_ref
+
+
+# --------------------------------------------------------------------------------------
+# autograd
+# --------------------------------------------------------------------------------------
+class _XViewFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg: XViewConfig, B: int, N: int, ref, attn_logits, offsets, cam_logits, lidar2img,
+                *values):
+        ref_c = _f32c(ref, "reference_points")
+        attn_c = _f32c(attn_logits, "attn_logits")
+        off_c = _f32c(offsets, "offsets")
+        cam_c = _f32c(cam_logits, "cam_logits")
+        l2i_c = _f32c(lidar2img, "lidar2img")
+        out, _ = xview_forward(cfg, values, B, N, ref_c, attn_c, off_c, cam_c, l2i_c)
+        ctx.cfg, ctx.B, ctx.N = cfg, B, N
+        ctx.has_off, ctx.has_cam = offsets is not None, cam_logits is not None
+        ctx.save_for_backward(ref_c, attn_c, off_c if off_c is not None else ref_c.new_empty(0),
+                              cam_c if cam_c is not None else ref_c.new_empty(0), l2i_c, *values)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ref, attn, off, cam, l2i, *values = ctx.saved_tensors
+        off = off if ctx.has_off else None
+        cam = cam if ctx.has_cam else None
+        nd = ctx.needs_input_grad
+        need_values = any(nd[8:])
+        grad_values = [torch.zeros(v.shape, device=v.device, dtype=torch.float32) for v in values] \
+            if need_values else None
+        g_attn, g_off, g_cam, g_ref = xview_backward(
+            ctx.cfg, values, ctx.B, ctx.N, ref, attn, off, cam, l2i, grad_out, grad_values,
+            need_ref=nd[3], need_offsets=ctx.has_off and nd[5])
+        gv = [None] * len(values)
+        if need_values:
+            gv = [g if g.dtype == v.dtype else g.to(v.dtype) for g, v in zip(grad_values, values)]
+        return (None, None, None, g_ref if nd[3] else None, g_attn if nd[4] else None,
+                g_off if (ctx.has_off and nd[5]) else None, g_cam if (ctx.has_cam and nd[6]) else None,
+                None, *gv)
+
+
+def xview_attention(cfg: XViewConfig, packed: PackedFeatures, ref, attn_logits, offsets=None,
+                    cam_logits=None, lidar2img=None, values: Optional[Sequence[torch.Tensor]] = None):
+    """Differentiable fused cross-view sampling attention -> (B,Q,C) fp32.
+
+    ``values`` overrides ``packed.levels`` (variant C passes the value_proj'ed maps)."""
+    vals = list(values) if values is not None else packed.levels
+    return _XViewFn.apply(cfg, packed.B, packed.N, ref, attn_logits, offsets, cam_logits, lidar2img, *vals)

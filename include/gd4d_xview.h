@@ -1,0 +1,140 @@
+/*
+ * gd4d_xview.h -- C ABI of the B200-native cross-view 3D->2D feature-sampling
+ * attention (Graph-DETR4D decoder hot path).
+ *
+ * Plain C, raw DEVICE pointers and sizes, a CUDA stream passed as void*; no
+ * torch types, no allocation, no device synchronisation, re-entrant.  Every
+ * entry point returns 0 on success or a negative gd4d_status; nothing throws
+ * across the boundary.  The shared library (libgd4d_xview.so) is built from
+ * graph_detr4d_b200/csrc/ for sm_100a only.
+ *
+ * Each entry point replaces one piece of the reference (paths relative to the
+ * reference repo, projects/mmdet3d_plugin/models/utils/):
+ *
+ *   gd4d_xview_forward   mode A : feature_sampling + sigmoid*mask + 3 sums
+ *                                 detr3d_transformer.py:376-383, 397-438
+ *                        mode C : 3D graph-offset points -> projection -> mask
+ *                                 -> softmax*mask -> MultiScaleDeformableAttn
+ *                                 -> per-camera sigmoid weight -> sum over cams
+ *                                 deform3d_cross_attn.py:227-258, 274, 281-284,
+ *                                 301-304, 320-324   (mmcv ms_deform_attn_forward)
+ *                        mode V2: per-(cam,head,level,point) 2D offsets
+ *                                 detr3d_transformer.py:602-627, 636-709
+ *   gd4d_xview_backward  what autograd + mmcv ms_deform_attn_backward +
+ *                        grid_sampler_2d_backward do for the same lines
+ *   gd4d_pack_nchw       the per-layer flatten/transpose/cat of the feature maps
+ *                        deform3d_cross_attn.py:264-269 (done ONCE per forward here)
+ */
+#ifndef GD4D_XVIEW_H_
+#define GD4D_XVIEW_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GD4D_API __attribute__((visibility("default")))
+#else
+#define GD4D_API
+#endif
+
+#define GD4D_ABI_VERSION 1
+#define GD4D_MAX_LEVELS 8
+
+typedef enum gd4d_status {
+  GD4D_OK = 0,
+  GD4D_ERR_NULL = -1,        /* required pointer is NULL                       */
+  GD4D_ERR_DIMS = -2,        /* non-positive / inconsistent dimension          */
+  GD4D_ERR_HEAD_DIM = -3,    /* C/Hh is not 32 (the only head width built)     */
+  GD4D_ERR_ALIGN = -4,       /* a feature/out pointer is not 16-byte aligned   */
+  GD4D_ERR_UNSUPPORTED = -5, /* unknown mode / dtype / L*P > 64 / N*P too big  */
+  GD4D_ERR_CUDA = -6         /* launch failed (cudaGetLastError != success)    */
+} gd4d_status;
+
+typedef enum gd4d_mode {
+  GD4D_MODE_A = 0,  /* Detr3DCrossAtten   (centre point, sigmoid weights per cam) */
+  GD4D_MODE_C = 1,  /* Deform3DCrossAttn  (3D offset points, softmax, cam weight) */
+  GD4D_MODE_V2 = 2  /* Detr3DCrossAttenV2 (2D offsets, softmax per cam & head)    */
+} gd4d_mode;
+
+typedef enum gd4d_dtype { GD4D_F32 = 0, GD4D_BF16 = 1 } gd4d_dtype;
+
+/*
+ * One decoder-layer invocation.  All pointers are device pointers.
+ *
+ * Feature maps ("value") are CHANNEL-LAST, one base pointer per FPN level:
+ *   value[l] : (B*N, level_h[l], level_w[l], C)   fp32 or bf16, 16-byte aligned
+ * with camera index n fastest inside the leading B*N axis (image = b*N + n),
+ * i.e. exactly torch's channels_last storage of the reference's
+ * feat.view(B*N, C, H, W), and exactly mmcv's (bs, num_keys, heads, dims) value
+ * layout taken level by level.
+ *
+ * Per-mode tensors (fp32, contiguous):
+ *            ref (B,Q,3) in [0,1]; lidar2img (B,N,4,4) row-major
+ *   mode A : attn_logits (B,Q,N,P,L)              offsets = cam_logits = NULL
+ *   mode C : attn_logits (B,Q,Hh,L,P)             offsets (B,Q,Hh,P,3) metres
+ *            cam_logits  (B, Q*N) raw Linear output; the kernel indexes it as the
+ *            reference's .view(B,N,Q,1) does: weight(n,q) = flat[n*Q + q]
+ *   mode V2: attn_logits (B,Q,N,Hh,L,P)           offsets (B,Q,N,Hh,L,P,2) pixels
+ * Activations (sigmoid / softmax) are applied inside the kernel.
+ *
+ * Outputs:  out (B,Q,C) fp32.
+ *           mask (optional, may be NULL) uint8: A/V2 (B,Q,N); C (B,N,Q,Hh,P).
+ *
+ * Backward (gd4d_xview_backward) reads grad_out (B,Q,C) and ACCUMULATES with
+ * atomics into caller-zeroed buffers; any grad pointer may be NULL to skip it:
+ *   grad_value[l] fp32 channel-last, same shape as value[l]
+ *   grad_attn_logits / grad_offsets / grad_cam_logits / grad_ref : as the inputs
+ */
+typedef struct gd4d_xview_params {
+  int32_t abi_version;          /* must be GD4D_ABI_VERSION */
+  int32_t mode;                 /* gd4d_mode  */
+  int32_t value_dtype;          /* gd4d_dtype */
+  int32_t B, Q, N, Hh, L, P, C;
+  int32_t level_h[GD4D_MAX_LEVELS];
+  int32_t level_w[GD4D_MAX_LEVELS];
+  float pc_lo[3];               /* pc_range[0:3]                              */
+  float pc_span[3];             /* float32(pc_range[3+i] - pc_range[i])       */
+  float img_h, img_w;           /* img_metas[0]['img_shape'][0][0:2], unpadded */
+  const void* value[GD4D_MAX_LEVELS];
+  const float* value_bias;      /* optional (C): bias of a value_proj folded into
+                                   the sampler: out += bias * sum(w * inbounds) */
+  const float* ref;
+  const float* lidar2img;
+  const float* attn_logits;
+  const float* offsets;
+  const float* cam_logits;
+  float* out;
+  uint8_t* mask;
+  /* backward only */
+  const float* grad_out;
+  float* grad_value[GD4D_MAX_LEVELS];
+  float* grad_value_bias;
+  float* grad_attn_logits;
+  float* grad_offsets;
+  float* grad_cam_logits;
+  float* grad_ref;
+} gd4d_xview_params;
+
+GD4D_API int gd4d_abi_version(void);
+GD4D_API const char* gd4d_strerror(int status);
+
+/* bytes of dynamic shared memory / CTAs the forward launch will use (for tests
+ * and the roofline bookkeeping); negative status on invalid params. */
+GD4D_API int gd4d_xview_launch_info(const gd4d_xview_params* p, int32_t* grid, int32_t* block,
+                           int32_t* smem_bytes);
+
+GD4D_API int gd4d_xview_forward(const gd4d_xview_params* p, void* cuda_stream);
+GD4D_API int gd4d_xview_backward(const gd4d_xview_params* p, void* cuda_stream);
+
+/* NCHW (images, C, H, W) -> channel-last (images, H, W, C) with optional cast.
+ * src_dtype/dst_dtype: gd4d_dtype (fp32->fp32, fp32->bf16, bf16->bf16). */
+GD4D_API int gd4d_pack_nchw(const void* src, void* dst, int32_t src_dtype, int32_t dst_dtype,
+                   int64_t images, int32_t C, int32_t H, int32_t W, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GD4D_XVIEW_H_ */

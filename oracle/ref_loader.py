@@ -1,0 +1,243 @@
+"""TEST INFRASTRUCTURE ONLY -- executes the *unmodified* reference code as the pin.
+
+Loads Graph-DETR4D's cross-view attention classes straight from
+``/root/reference`` (read-only) without mmcv/mmdet/mmdet3d being installed, by
+putting ~40 lines of ``sys.modules`` shims in place (SURVEY.md section 8c,
+Appendix C).  Nothing is copied: the reference sources are read where they lie
+and executed.  This module only works in the build container; the GPU box has
+no ``/root/reference``, which is why the outputs are frozen into
+``tests/golden/*.npz`` by ``tests/golden/make_golden.py``.
+
+What is loaded (reference file:line):
+  * ``feature_sampling``                 detr3d_transformer.py:397-438
+  * ``Detr3DCrossAtten``                 detr3d_transformer.py:229-390
+  * ``Detr3DCrossAttenV2``               detr3d_transformer.py:441-709
+  * ``Deform3DCrossAttn``                deform3d_cross_attn.py:33-339
+        The shipped non-CUDA branch (deform3d_cross_attn.py:305-309) raises
+        NameError (``sampling_locations`` is undefined).  ``variant="cpu"``
+        applies ONE documented token substitution in that call
+        (``sampling_locations`` -> ``reference_points_cam``) so the class runs
+        on CPU through mmcv's public grid_sample formulation of multi-scale
+        deformable attention (re-stated in ``_msda_pytorch`` below from mmcv
+        1.x ``mmcv/ops/multi_scale_deform_attn.py::multi_scale_deformable_attn_pytorch``;
+        mmcv is a third-party dependency that is NOT vendored in the reference
+        and whose version the reference does not pin).
+
+Only ``tests/`` and ``tests/golden/make_golden.py`` import this file.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REF_ROOT = os.environ.get("GD4D_REFERENCE_ROOT", "/root/reference")
+REF_UTILS = os.path.join(REF_ROOT, "projects", "mmdet3d_plugin", "models", "utils")
+_PKG = "gd4d_refutils"
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_UTILS, "detr3d_transformer.py"))
+
+
+# --------------------------------------------------------------------------
+# mmcv's public pure-PyTorch multi-scale deformable attention (grid_sample form)
+# --------------------------------------------------------------------------
+def _msda_pytorch(value, value_spatial_shapes, sampling_locations, attention_weights):
+    """mmcv 1.x ``multi_scale_deformable_attn_pytorch`` (third-party, restated).
+
+    value (bs, num_keys, heads, dims); shapes (L,2) as (h,w);
+    sampling_locations (bs, Q, heads, L, P, 2) in [0,1]; weights (bs,Q,heads,L,P).
+    """
+    bs, _, num_heads, embed_dims = value.shape
+    _, num_queries, num_heads, num_levels, num_points, _ = sampling_locations.shape
+    value_list = value.split([int(H_) * int(W_) for H_, W_ in value_spatial_shapes], dim=1)
+    sampling_grids = 2 * sampling_locations - 1
+    sampling_value_list = []
+    for level, (H_, W_) in enumerate(value_spatial_shapes):
+        H_, W_ = int(H_), int(W_)
+        value_l_ = value_list[level].flatten(2).transpose(1, 2).reshape(
+            bs * num_heads, embed_dims, H_, W_)
+        sampling_grid_l_ = sampling_grids[:, :, :, level].transpose(1, 2).flatten(0, 1)
+        sampling_value_l_ = F.grid_sample(
+            value_l_, sampling_grid_l_, mode="bilinear", padding_mode="zeros",
+            align_corners=False)
+        sampling_value_list.append(sampling_value_l_)
+    attention_weights = attention_weights.transpose(1, 2).reshape(
+        bs * num_heads, 1, num_queries, num_levels * num_points)
+    output = (torch.stack(sampling_value_list, dim=-2).flatten(-2) * attention_weights
+              ).sum(-1).view(bs, num_heads * embed_dims, num_queries)
+    return output.transpose(1, 2).contiguous()
+
+
+class _MSDAFunction:
+    """Stand-in for mmcv's CUDA autograd Function: same maths via grid_sample."""
+
+    @staticmethod
+    def apply(value, spatial_shapes, level_start_index, sampling_locations,
+              attention_weights, im2col_step):
+        return _msda_pytorch(value, spatial_shapes, sampling_locations, attention_weights)
+
+
+class _Registry:
+    def __init__(self, name):
+        self.name = name
+        self.module_dict = {}
+
+    def register_module(self, name=None, force=False, module=None):
+        def deco(cls):
+            self.module_dict[name or cls.__name__] = cls
+            return cls
+        if module is not None:
+            return deco(module)
+        return deco
+
+    def get(self, key):
+        return self.module_dict.get(key)
+
+
+class _BaseModule(nn.Module):
+    def __init__(self, init_cfg=None):
+        super().__init__()
+        self.init_cfg = init_cfg
+
+
+def _xavier_init(module, gain=1, bias=0, distribution="normal"):
+    if hasattr(module, "weight") and module.weight is not None:
+        if distribution == "uniform":
+            nn.init.xavier_uniform_(module.weight, gain=gain)
+        else:
+            nn.init.xavier_normal_(module.weight, gain=gain)
+    if hasattr(module, "bias") and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+def _constant_init(module, val, bias=0):
+    if hasattr(module, "weight") and module.weight is not None:
+        nn.init.constant_(module.weight, val)
+    if hasattr(module, "bias") and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+def _mod(name, **attrs):
+    m = sys.modules.get(name)
+    if m is None:
+        m = types.ModuleType(name)
+        m.__gd4d_shim__ = True
+        sys.modules[name] = m
+        if "." in name:
+            parent, _, leaf = name.rpartition(".")
+            setattr(_mod(parent), leaf, m)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    return m
+
+
+_REGS = {}
+
+
+def install_shims():
+    """Install import shims for mmcv / mmdet / mmdet3d (idempotent)."""
+    if _REGS:
+        return _REGS
+    attention = _Registry("attention")
+    tls = _Registry("transformer_layer_sequence")
+    transformer = _Registry("transformer")
+    _REGS.update(ATTENTION=attention, TRANSFORMER_LAYER_SEQUENCE=tls, TRANSFORMER=transformer)
+
+    class TransformerLayerSequence(_BaseModule):
+        def __init__(self, transformerlayers=None, num_layers=None, init_cfg=None):
+            super().__init__(init_cfg)
+            self.num_layers = num_layers
+            self.layers = nn.ModuleList()
+
+    class MultiScaleDeformableAttention(_BaseModule):
+        pass
+
+    _mod("mmcv")
+    _mod("mmcv.cnn", xavier_init=_xavier_init, constant_init=_constant_init)
+    _mod("mmcv.cnn.bricks")
+    _mod("mmcv.cnn.bricks.registry", ATTENTION=attention, TRANSFORMER_LAYER_SEQUENCE=tls)
+    _mod("mmcv.cnn.bricks.transformer",
+         MultiScaleDeformableAttention=MultiScaleDeformableAttention,
+         TransformerLayerSequence=TransformerLayerSequence,
+         build_transformer_layer_sequence=lambda cfg, *a, **k: None)
+    _mod("mmcv.runner")
+    _mod("mmcv.runner.base_module", BaseModule=_BaseModule)
+    _mod("mmcv.ops")
+    _mod("mmcv.ops.multi_scale_deform_attn",
+         MultiScaleDeformableAttnFunction=_MSDAFunction,
+         multi_scale_deformable_attn_pytorch=_msda_pytorch)
+    _mod("mmdet3d")
+    _mod("mmdet3d.core")
+    _mod("mmdet3d.core.bbox")
+    _mod("mmdet3d.core.bbox.structures")
+    _mod("mmdet3d.core.bbox.structures.utils", rotation_3d_in_axis=None)
+    _mod("mmdet")
+    _mod("mmdet.models")
+    _mod("mmdet.models.utils")
+    _mod("mmdet.models.utils.builder", TRANSFORMER=transformer)
+    _mod("mmdet.models.utils.transformer")
+    pkg = _mod(_PKG)
+    pkg.__path__ = [REF_UTILS]
+    return _REGS
+
+
+def _load_file(modname, filename, patch=None):
+    full = f"{_PKG}.{modname}"
+    if full in sys.modules and patch is None:
+        return sys.modules[full]
+    path = os.path.join(REF_UTILS, filename)
+    if patch is None:
+        spec = importlib.util.spec_from_file_location(full, path)
+        module = importlib.util.module_from_spec(spec)
+        sys.modules[full] = module
+        spec.loader.exec_module(module)
+        return module
+    src = open(path).read()
+    src = patch(src)
+    module = types.ModuleType(full + "_patched")
+    module.__file__ = path
+    module.__package__ = _PKG
+    exec(compile(src, path, "exec"), module.__dict__)
+    return module
+
+
+_DC_CALL = "value_flatten, spatial_shapes, sampling_locations, attention_weights)"
+
+
+def _patch_dc(src):
+    # the one documented token substitution (deform3d_cross_attn.py:308-309)
+    assert src.count(_DC_CALL) == 1, "reference source changed; re-audit the patch"
+    return src.replace(_DC_CALL, _DC_CALL.replace("sampling_locations", "reference_points_cam"))
+
+
+def load():
+    """Return a namespace with the reference symbols.
+
+    ``Deform3DCrossAttn``      -- unmodified class (runs its CUDA branch on a GPU
+                                   through the shimmed MSDA function)
+    ``Deform3DCrossAttnCPU``   -- same file with the one-token fix, runs on CPU
+    """
+    if not available():
+        raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+    install_shims()
+    dc = _load_file("deform3d_cross_attn", "deform3d_cross_attn.py")
+    dt = _load_file("detr3d_transformer", "detr3d_transformer.py")
+    dc_cpu = _load_file("deform3d_cross_attn", "deform3d_cross_attn.py", patch=_patch_dc)
+    ns = types.SimpleNamespace(
+        feature_sampling=dt.feature_sampling,
+        inverse_sigmoid=dt.inverse_sigmoid,
+        Detr3DCrossAtten=dt.Detr3DCrossAtten,
+        Detr3DCrossAttenV2=dt.Detr3DCrossAttenV2,
+        Deform3DCrossAttn=dc.Deform3DCrossAttn,
+        Deform3DCrossAttnCPU=dc_cpu.Deform3DCrossAttn,
+        msda_pytorch=_msda_pytorch,
+        registries=_REGS,
+    )
+    return ns

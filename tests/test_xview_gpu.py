@@ -1,0 +1,179 @@
+"""GPU parity: the fused sm_100a kernels (through the C ABI) vs the CPU oracle.
+
+Tolerances (BASELINE.json north_star):
+  fp32 features : max|out - ref| <= 1e-5 * max|ref|
+  bf16 features : same 1e-5 bound vs the oracle fed the SAME bf16-rounded features
+                  (all kernel math is fp32), and <= 8e-3 * max|ref| vs the fp32 oracle
+  mask          : bit-exact
+  gradients     : <= 2e-4 * max|ref| (fp32 atomics reorder sums; the oracle's own
+                  autograd accumulates in a different order)
+"""
+import pytest
+import torch
+
+from graph_detr4d_b200 import ops
+from graph_detr4d_b200.ops import MODE_A, MODE_C, XViewConfig
+from graph_detr4d_b200 import synthetic as syn
+from oracle import xview_oracle as xo
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+FWD_TOL = 1e-5
+BF16_TOL = 8e-3
+GRAD_TOL = 2e-4
+
+
+def _pack(feats, dtype=None):
+    return ops.pack_features([f.cuda() for f in feats], dtype)
+
+
+@pytest.mark.parametrize("B,T,Q,P", [(1, 1, 128, 1), (2, 2, 77, 1), (1, 1, 64, 3)])
+def test_mode_a_forward_and_mask(B, T, Q, P):
+    sc = H.scene(B=B, T=T, Q=Q)
+    logits = H.rand_inputs_a(sc, P=P)
+    ref_out, ref_mask = xo.xview_a_core(sc["feats"], sc["ref"], logits, sc["l2i"], syn.PC_RANGE, 900, 1600)
+    packed = _pack(sc["feats"])
+    cfg = XViewConfig(MODE_A, 8, P, tuple(syn.PC_RANGE), 900.0, 1600.0)
+    out, mask = ops.xview_forward(cfg, packed.levels, B, sc["N"], sc["ref"].cuda(), logits.cuda(),
+                                  lidar2img=sc["l2i"].cuda(), want_mask=True)
+    assert torch.equal(mask.cpu().bool(), ref_mask), "projection mask must be bit-exact"
+    assert ref_mask.any()
+    assert H.rel_err(out.cpu(), ref_out) <= FWD_TOL
+
+
+@pytest.mark.parametrize("B,T,Q,P", [(1, 2, 128, 4), (2, 1, 50, 4), (1, 1, 33, 1), (1, 2, 40, 8)])
+def test_mode_c_forward_and_mask(B, T, Q, P):
+    sc = H.scene(B=B, T=T, Q=Q)
+    logits, offsets, cam = H.rand_inputs_c(sc, P=P)
+    ref_out, ref_mask = xo.xview_c_core(sc["feats"], sc["ref"], offsets, logits, cam, sc["l2i"],
+                                        syn.PC_RANGE, 900, 1600, 8)
+    packed = _pack(sc["feats"])
+    cfg = XViewConfig(MODE_C, 8, P, tuple(syn.PC_RANGE), 900.0, 1600.0)
+    out, mask = ops.xview_forward(cfg, packed.levels, B, sc["N"], sc["ref"].cuda(), logits.cuda(),
+                                  offsets.cuda(), cam.cuda(), sc["l2i"].cuda(), want_mask=True)
+    # oracle mask is (B,N,Q,Hh,L,P), identical over L (offsets are shared across levels)
+    assert torch.equal(ref_mask[:, :, :, :, 0, :], ref_mask[:, :, :, :, -1, :])
+    assert torch.equal(mask.cpu().bool(), ref_mask[:, :, :, :, 0, :]), "projection mask must be bit-exact"
+    assert ref_mask.any()
+    assert H.rel_err(out.cpu(), ref_out) <= FWD_TOL
+
+
+@pytest.mark.parametrize("mode", ["A", "C"])
+def test_bf16_features(mode):
+    sc = H.scene(B=1, T=2, Q=96)
+    feats_bf = [f.to(torch.bfloat16) for f in sc["feats"]]
+    feats_rounded = [f.float() for f in feats_bf]
+    packed = _pack(sc["feats"], torch.bfloat16)
+    assert packed.levels[0].dtype == torch.bfloat16
+    if mode == "A":
+        logits = H.rand_inputs_a(sc)
+        ref_same, _ = xo.xview_a_core(feats_rounded, sc["ref"], logits, sc["l2i"], syn.PC_RANGE, 900, 1600)
+        ref_full, _ = xo.xview_a_core(sc["feats"], sc["ref"], logits, sc["l2i"], syn.PC_RANGE, 900, 1600)
+        cfg = XViewConfig(MODE_A, 8, 1, tuple(syn.PC_RANGE), 900.0, 1600.0)
+        out, _ = ops.xview_forward(cfg, packed.levels, 1, sc["N"], sc["ref"].cuda(), logits.cuda(),
+                                   lidar2img=sc["l2i"].cuda())
+    else:
+        logits, offsets, cam = H.rand_inputs_c(sc)
+        ref_same, _ = xo.xview_c_core(feats_rounded, sc["ref"], offsets, logits, cam, sc["l2i"],
+                                      syn.PC_RANGE, 900, 1600, 8)
+        ref_full, _ = xo.xview_c_core(sc["feats"], sc["ref"], offsets, logits, cam, sc["l2i"],
+                                      syn.PC_RANGE, 900, 1600, 8)
+        cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0)
+        out, _ = ops.xview_forward(cfg, packed.levels, 1, sc["N"], sc["ref"].cuda(), logits.cuda(),
+                                   offsets.cuda(), cam.cuda(), sc["l2i"].cuda())
+    assert H.rel_err(out.cpu(), ref_same) <= FWD_TOL
+    assert H.rel_err(out.cpu(), ref_full) <= BF16_TOL
+
+
+def _leaf(t):
+    return t.clone().requires_grad_(True)
+
+
+@pytest.mark.parametrize("B,T,Q,P", [(1, 1, 96, 1), (2, 1, 40, 2)])
+def test_mode_a_backward(B, T, Q, P):
+    sc = H.scene(B=B, T=T, Q=Q)
+    logits = H.rand_inputs_a(sc, P=P)
+    g = torch.Generator().manual_seed(9)
+    gout = torch.randn(B, Q, sc["C"], generator=g)
+    # oracle autograd
+    feats_o = [_leaf(f) for f in sc["feats"]]
+    ref_o, log_o = _leaf(sc["ref"]), _leaf(logits)
+    out_o, _ = xo.xview_a_core(feats_o, ref_o, log_o, sc["l2i"], syn.PC_RANGE, 900, 1600)
+    out_o.backward(gout)
+    # product
+    feats_g = [_leaf(f.cuda()) for f in sc["feats"]]
+    ref_g, log_g = _leaf(sc["ref"].cuda()), _leaf(logits.cuda())
+    packed = ops.pack_features(feats_g)
+    cfg = XViewConfig(MODE_A, 8, P, tuple(syn.PC_RANGE), 900.0, 1600.0)
+    out = ops.xview_attention(cfg, packed, ref_g, log_g, lidar2img=sc["l2i"].cuda())
+    out.backward(gout.cuda())
+    assert H.rel_err(out.detach().cpu(), out_o.detach()) <= FWD_TOL
+    assert H.rel_err(log_g.grad.cpu(), log_o.grad) <= GRAD_TOL
+    assert H.rel_err(ref_g.grad.cpu(), ref_o.grad) <= GRAD_TOL
+    for fg, fo in zip(feats_g, feats_o):
+        assert fg.grad.shape == fo.grad.shape
+        assert H.rel_err(fg.grad.cpu(), fo.grad) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("B,T,Q,P,dtype", [(1, 2, 96, 4, torch.float32), (2, 1, 30, 2, torch.float32),
+                                           (1, 2, 64, 4, torch.bfloat16)])
+def test_mode_c_backward(B, T, Q, P, dtype):
+    sc = H.scene(B=B, T=T, Q=Q)
+    logits, offsets, cam = H.rand_inputs_c(sc, P=P)
+    g = torch.Generator().manual_seed(9)
+    gout = torch.randn(B, Q, sc["C"], generator=g)
+    feats_src = [f.to(dtype).float() for f in sc["feats"]]      # bf16 case: same rounded features
+    feats_o = [_leaf(f) for f in feats_src]
+    ref_o, log_o, off_o, cam_o = _leaf(sc["ref"]), _leaf(logits), _leaf(offsets), _leaf(cam)
+    out_o, _ = xo.xview_c_core(feats_o, ref_o, off_o, log_o, cam_o, sc["l2i"], syn.PC_RANGE, 900, 1600, 8)
+    out_o.backward(gout)
+
+    feats_g = [_leaf(f.cuda()) for f in feats_src]
+    ref_g, log_g, off_g, cam_g = (_leaf(t.cuda()) for t in (sc["ref"], logits, offsets, cam))
+    packed = ops.pack_features(feats_g, dtype)
+    cfg = XViewConfig(MODE_C, 8, P, tuple(syn.PC_RANGE), 900.0, 1600.0)
+    out = ops.xview_attention(cfg, packed, ref_g, log_g, off_g, cam_g, sc["l2i"].cuda())
+    out.backward(gout.cuda())
+    assert H.rel_err(out.detach().cpu(), out_o.detach()) <= FWD_TOL
+    assert H.rel_err(log_g.grad.cpu(), log_o.grad) <= GRAD_TOL
+    assert H.rel_err(cam_g.grad.cpu(), cam_o.grad) <= GRAD_TOL
+    assert H.rel_err(off_g.grad.cpu(), off_o.grad) <= GRAD_TOL
+    assert H.rel_err(ref_g.grad.cpu(), ref_o.grad) <= GRAD_TOL
+    gtol = GRAD_TOL if dtype == torch.float32 else 1e-2        # grads are cast to bf16 on the way back
+    for fg, fo in zip(feats_g, feats_o):
+        assert H.rel_err(fg.grad.cpu().float(), fo.grad) <= gtol
+
+
+def test_pack_is_exact_and_zero_copy_for_channels_last():
+    sc = H.scene(B=2, T=1, Q=8)
+    f = sc["feats"][0].cuda()
+    packed = ops.pack_level(f)
+    B, N, C, Hh, W = f.shape
+    assert torch.equal(packed, f.flatten(0, 1).permute(0, 2, 3, 1).contiguous())
+    f_cl = f.flatten(0, 1).contiguous(memory_format=torch.channels_last).unflatten(0, (B, N))
+    p2 = ops.pack_level(f_cl)
+    assert p2.data_ptr() == f_cl.data_ptr()
+    assert torch.equal(p2, packed)
+    pb = ops.pack_level(f, torch.bfloat16)
+    assert torch.equal(pb, packed.to(torch.bfloat16))
+
+
+def test_no_cpu_fallback():
+    sc = H.scene(B=1, T=1, Q=8)
+    with pytest.raises(RuntimeError):
+        ops.pack_features(sc["feats"])          # CPU tensors must be refused, not silently computed
+
+
+def test_error_codes():
+    from graph_detr4d_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    p = _lib.XViewParams()
+    assert lib.gd4d_xview_forward(None, None) == -1
+    p.abi_version = 99
+    assert lib.gd4d_xview_forward(C.byref(p), None) == -5
+    p.abi_version = _lib.ABI_VERSION
+    assert lib.gd4d_xview_forward(C.byref(p), None) == -2       # all dims zero
+    p.B = p.Q = p.N = p.L = p.P = 1
+    p.Hh, p.C = 8, 128                                           # head width 16
+    assert lib.gd4d_xview_forward(C.byref(p), None) == -3
