@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the cross-view sampling attention path.
+
+Workload (BASELINE.json configs[1]): the Graph-DETR3D 6-layer decoder (variant C
+attention, single frame: 6 cameras, 900 queries, 4 FPN levels x 256 ch of a
+928x1600 input), forward + backward (+ AdamW step), batch 1 per GPU, synthetic
+features and random-init weights.  One "step" = one such training pass.
+
+metric  = cross-view attention queries/s = B*Q*num_layers / step time
+          (query-layer evaluations: SURVEY 8d normalises per decoder-layer invocation)
+value   = inputs resident in HBM when the timed region starts
+e2e     = same through the public module API with HOST buffers: the step's feature
+          maps are copied H2D from pinned memory and the loss is read back D2H
+          inside the timed region
+roofline= the dominant hand-written kernel (fused backward), timed live with CUDA
+          events on the launching stream, algorithmic bytes / time vs measured HBM peak
+cpu_baseline / --impl reference: the CPU oracle port of the same decoder layer
+          timed on this box's host cores (bounded sample: ONE decoder layer).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...      (weak scaling, DDP/NCCL)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "cross_view_attn_queries_per_s"
+UNIT = "queries/s"
+Q, C, HEADS, LEVELS, POINTS, LAYERS = 900, 256, 8, 4, 4, 6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="feature-map dtype")
+    ap.add_argument("--frames", type=int, default=1, help="temporal frames T (cameras = 6T)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(T, dtype):
+    return f"graph_detr3d_decoder6_fwd_bwd_B1_Q{Q}_N{6 * T}_L4x{C}ch_928x1600_{dtype}"
+
+
+def attn_cfg(T, dtype):
+    from graph_detr4d_b200 import synthetic as syn
+    cfg = dict(type="Deform3DCrossAttn", embed_dims=C, num_heads=HEADS, num_levels=LEVELS,
+               num_points=POINTS, num_cams=6 * T, pc_range=syn.PC_RANGE, dropout=0.0)
+    if dtype == "bf16":
+        cfg["feature_dtype"] = "bf16"
+    return cfg
+
+
+def build_model(T, dtype, device, layers=LAYERS, factory=None, seed=0):
+    from graph_detr4d_b200 import synthetic as syn
+    from graph_detr4d_b200.decoder import Detr3DTransformer, Detr3DTransformerDecoder
+    torch.manual_seed(seed)
+    cfg = attn_cfg(T, dtype)
+    if factory is not None:
+        cfg.pop("feature_dtype", None)
+    dec = Detr3DTransformerDecoder(cfg, num_layers=layers, embed_dims=C, num_heads=HEADS, dropout=0.0,
+                                   cross_attn_factory=factory)
+    model = Detr3DTransformer(dec, num_query=Q)
+    for i, layer in enumerate(dec.layers):
+        syn.randomize_generators(layer.attentions[1], std=0.05, seed=100 + i)
+    return model.to(device)
+
+
+_LOSS_W = {}
+
+
+def loss_fn(states, refs):
+    """Synthetic scalar loss over every layer's output (the Hungarian loss is out of
+    scope): a fixed random projection.  (mean(states^2) would be a constant right after
+    the final LayerNorm -- a degenerate loss with rounding-noise gradients.)"""
+    key = (states.device, tuple(states.shape))
+    if key not in _LOSS_W:
+        g = torch.Generator().manual_seed(1234)
+        _LOSS_W[key] = torch.randn(states.shape, generator=g).to(states.device)
+    return (states.float() * _LOSS_W[key]).mean() + refs.float().mean() * 0.0
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe) during the timed region
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline (oracle port) -- the reference arm and the cpu_baseline leg
+# --------------------------------------------------------------------------------------
+def cpu_layer_time(T, runs, warmup):
+    """ONE decoder layer (self-attn + cross-view attention + FFN) fwd+bwd on the host
+    cores with the oracle's port of Deform3DCrossAttn.  Returns seconds per run."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from graph_detr4d_b200 import synthetic as syn
+    from oracle.modules_port import build_oracle_attention          # bench may execute oracle/ HERE only
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = build_model(T, "f32", "cpu", layers=1, factory=build_oracle_attention)
+    feats = [f.requires_grad_(True) for f in syn.make_feats(1, 6 * T, C, syn.LEVEL_SHAPES_928x1600, seed=0)]
+    metas = syn.make_img_metas(1, T)
+    times = []
+    for i in range(warmup + runs):
+        t0 = time.perf_counter()
+        states, _, refs = model(feats, metas, 1)
+        loss_fn(states, refs).backward()
+        dt = time.perf_counter() - t0
+        model.zero_grad(set_to_none=True)
+        for f in feats:
+            f.grad = None
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    return times[len(times) // 2], cores, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T = args.frames
+    runs = max(1, min(args.steps, 20))
+    t, cores, threads = cpu_layer_time(T, runs, max(1, min(args.warmup, 3)))
+    val = Q / t
+    sample = f"1 of {LAYERS} decoder layers (self-attn + Deform3DCrossAttn + FFN) fwd+bwd per step, B=1, Q={Q}"
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=runs, warmup=args.warmup,
+                ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=workload_name(T, "f32"), sample=sample),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port", sample=sample,
+                                  host_cpus=cores),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    from graph_detr4d_b200 import _lib, modules, ops, roofline, synthetic as syn
+    _lib.load(build_if_missing=False)            # fail loudly: no CUDA library, no benchmark
+    T, dtype = args.frames, args.dtype
+    N = 6 * T
+    model = build_model(T, dtype, dev, seed=0)              # identical replicas on every rank
+    feats_host = [f.pin_memory() for f in syn.make_feats(1, N, C, syn.LEVEL_SHAPES_928x1600, seed=rank)]
+    feats_dev = [f.to(dev) for f in feats_host]
+    metas = syn.make_img_metas(1, T)
+    h2d_bytes = sum(f.numel() * f.element_size() for f in feats_host)
+
+    def forward_loss(feats):
+        states, _, refs = model(feats, metas, 1)
+        return loss_fn(states, refs)
+
+    # The whole step (fwd + bwd + AdamW) is captured in CUDA graphs; the gradient
+    # all-reduce (N>1) is one NCCL call on a flat buffer between the two graphs.
+    from graph_detr4d_b200.graphed import GraphedTrainStep
+    calls0 = ops.launch_count()
+    stepper = GraphedTrainStep(model, forward_loss, feats_dev, metas, world_size=world)
+    launches_per_step = (ops.launch_count() - calls0) // 4   # 3 eager warm-ups + 1 capture
+
+    def step_resident():
+        return stepper.step()
+
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        stepper.set_inputs(feats_host, metas)               # H2D of this step's feature maps (pinned)
+        loss = stepper.step()
+        loss_host.copy_(loss, non_blocking=True)            # D2H of the step's result
+        torch.cuda.current_stream().synchronize()           # the user reads the loss every step
+        return float(loss_host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total = timed(step_resident, K)
+    launches = launches_per_step * K
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, K)
+    clocks = sampler.stop()
+    feats_dev = stepper.static_feats
+
+    units = world * Q * LAYERS                       # query-layer evaluations per step, all ranks
+    value = units * K / (ms_total * 1e-3)
+    e2e_val = units * K / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant hand-written kernel, timed live -------------------------
+    roof = roof_fwd = None
+    if rank == 0:
+        roof, roof_fwd = kernel_roofline(model, feats_dev, metas, T, dtype, dev)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t, cores, threads = cpu_layer_time(T, runs=5, warmup=1)
+        cpu_base = dict(value=Q / t, unit=UNIT, cores=threads, kind="port", host_cpus=cores,
+                        ms_per_layer=t * 1e3,
+                        sample=f"1 of {LAYERS} decoder layers fwd+bwd (oracle port, torch CPU), median of 5")
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype=dtype, data="synthetic",
+                    config=dict(workload=workload_name(T, dtype), layers=LAYERS, queries=Q, cams=N,
+                                points=POINTS, heads=HEADS, per_gpu_batch=1, optimizer="AdamW(fused)",
+                                parallelism=f"dp{world}" if world > 1 else "single",
+                                l2="inputs larger than L2 (feature maps + dense grad maps >= 2x126 MB per layer)"),
+                    e2e=dict(value=e2e_val, unit=UNIT, ms_per_step=ms_e2e / K,
+                             h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),
+                    gpu_launches=launches, clocks=clocks, roofline=roof, roofline_fwd=roof_fwd,
+                    cpu_baseline=cpu_base)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(model, feats_dev, metas, T, dtype, dev):
+    """Times the fused fwd and bwd kernels alone at the workload's layer-0 inputs:
+    CUDA events on the launching (current) stream around back-to-back launches that
+    rotate over 3 copies of the value maps so consecutive launches do not hit L2."""
+    from graph_detr4d_b200 import modules, ops, roofline
+    from graph_detr4d_b200.ops import MODE_C, XViewConfig
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    attn = model.decoder.layers[0].attentions[1]
+    N = 6 * T
+    with torch.no_grad():
+        qe = model.query_embedding.weight
+        query_pos, query = torch.split(qe, C, dim=1)
+        q = (query + query_pos).unsqueeze(0)
+        ref = model.reference_points(query_pos.unsqueeze(0)).sigmoid().contiguous()
+        cam = attn.cam_attention_weights(q).contiguous()
+        off = attn.deform_sampling_offsets(q).contiguous()
+        log = attn.attention_weights(q).contiguous()
+        packed = ops.pack_features([f.detach() for f in feats_dev], attn.feature_dtype)
+        wide = attn._use_wide(packed)
+        sets = []
+        for _ in range(3):
+            src = packed.levels if wide else attn.project_values(packed)
+            sets.append([v.clone() for v in src])
+        l2i = ops.lidar2img_to_tensor(metas, dev)
+        cfg = XViewConfig(MODE_C, HEADS, POINTS, tuple(attn.pc_range), 900.0, 1600.0, wide=wide)
+        shapes = packed.shapes
+        stats = roofline.count_corner_reads(MODE_C, shapes, ref, off, l2i, attn.pc_range, 900.0, 1600.0,
+                                            HEADS, POINTS)
+        eb = 2 if sets[0][0].dtype == torch.bfloat16 else 4
+        ab = roofline.algorithmic_bytes(MODE_C, stats, 1, Q, N, C, HEADS, LEVELS, POINTS, eb, wide=wide)
+        gout = torch.randn((1, Q, HEADS, C) if wide else (1, Q, C), device=dev)
+        gws = torch.randn(1, Q, HEADS, device=dev) if wide else None
+        gsets = [[torch.zeros(v.shape, device=dev, dtype=torch.float32) for v in s] for s in sets]
+        reps = 60
+
+        def time_loop(fn):
+            for i in range(6):
+                fn(i % 3)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for i in range(reps):
+                fn(i % 3)
+            e.record()
+            torch.cuda.synchronize()
+            return s.elapsed_time(e) / reps * 1e-3
+
+        fwd_prep = [ops.prepare_forward(cfg, s, 1, N, ref, log, off, cam, l2i) for s in sets]
+        bwd_prep = [ops.prepare_backward(cfg, s, 1, N, ref, log, off, cam, l2i, gout, g, grad_wsum=gws)
+                    for s, g in zip(sets, gsets)]
+        t_f = time_loop(lambda i: fwd_prep[i].launch())
+        t_b = time_loop(lambda i: bwd_prep[i].launch())
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"N{N}_{dtype}", {})
+
+    def obj(name, t, nbytes, key):
+        ach = nbytes / t / 1e9
+        return dict(kernel=name, bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                    traffic=traffic.get(key), algorithmic_bytes=nbytes, us_per_launch=t * 1e6,
+                    peak_source=peak_src, corner_reads=ab["S"], valid_fraction=stats["valid_fraction"],
+                    timing=f"{reps} back-to-back launches, CUDA events on the launch stream, 3 rotating "
+                           f"value-map copies (footprint > L2)")
+    tag = "C,wide" if wide else "C,narrow"
+    return (obj(f"xview_bwd_kernel<{tag}>", t_b, ab["bwd"], "bwd"),
+            obj(f"xview_fwd_kernel<{tag}>", t_f, ab["fwd"], "fwd"))
+
+
+if __name__ == "__main__":
+    main()

@@ -13,13 +13,14 @@ import threading
 
 from . import _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LEVELS = 8
 MODE_A, MODE_C, MODE_V2 = 0, 1, 2
 F32, BF16 = 0, 1
 
 EXPORTS = (
     "gd4d_abi_version",
+    "gd4d_params_size",
     "gd4d_strerror",
     "gd4d_xview_launch_info",
     "gd4d_xview_forward",
@@ -36,6 +37,7 @@ class XViewParams(C.Structure):
         ("value_dtype", C.c_int32),
         ("B", C.c_int32), ("Q", C.c_int32), ("N", C.c_int32), ("Hh", C.c_int32),
         ("L", C.c_int32), ("P", C.c_int32), ("C", C.c_int32),
+        ("wide", C.c_int32),
         ("level_h", C.c_int32 * MAX_LEVELS),
         ("level_w", C.c_int32 * MAX_LEVELS),
         ("pc_lo", C.c_float * 3),
@@ -49,8 +51,10 @@ class XViewParams(C.Structure):
         ("offsets", C.c_void_p),
         ("cam_logits", C.c_void_p),
         ("out", C.c_void_p),
+        ("wsum", C.c_void_p),
         ("mask", C.c_void_p),
         ("grad_out", C.c_void_p),
+        ("grad_wsum", C.c_void_p),
         ("grad_value", C.c_void_p * MAX_LEVELS),
         ("grad_value_bias", C.c_void_p),
         ("grad_attn_logits", C.c_void_p),
@@ -102,8 +106,12 @@ def load(build_if_missing: bool = True):
         lib.gd4d_pack_nchw.restype = C.c_int
         lib.gd4d_pack_nchw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        lib.gd4d_params_size.restype = C.c_int
+        lib.gd4d_params_size.argtypes = []
         if lib.gd4d_abi_version() != ABI_VERSION:
             raise RuntimeError("libgd4d_xview.so ABI version mismatch; rebuild")
+        if lib.gd4d_params_size() != C.sizeof(XViewParams):
+            raise RuntimeError("gd4d_xview_params layout mismatch between the header and _lib.XViewParams")
         _lib = lib
     return _lib
 

@@ -18,8 +18,16 @@ static int validate(const gd4d_xview_params* p, bool backward, LaunchGeom* g) {
   if (p->B <= 0 || p->Q <= 0 || p->N <= 0 || p->Hh <= 0 || p->L <= 0 || p->P <= 0 || p->C <= 0)
     return GD4D_ERR_DIMS;
   if (p->L > GD4D_MAX_LEVELS || p->P > 255 || p->N >= (1 << 22)) return GD4D_ERR_DIMS;
-  if (p->C % p->Hh != 0) return GD4D_ERR_DIMS;
-  if (p->C / p->Hh != kHeadDim) return GD4D_ERR_HEAD_DIM;
+  g->nv = 1;
+  if (p->wide) {
+    if (p->mode != GD4D_MODE_C) return GD4D_ERR_UNSUPPORTED;
+    const long long row_bytes = static_cast<long long>(p->C) * (p->value_dtype == GD4D_BF16 ? 2 : 4);
+    if (row_bytes != 512 && row_bytes != 1024) return GD4D_ERR_HEAD_DIM;
+    g->nv = static_cast<int>(row_bytes / 512);
+  } else {
+    if (p->C % p->Hh != 0) return GD4D_ERR_DIMS;
+    if (p->C / p->Hh != kHeadDim) return GD4D_ERR_HEAD_DIM;
+  }
   if (!(p->img_h > 0.f) || !(p->img_w > 0.f)) return GD4D_ERR_DIMS;
   for (int l = 0; l < p->L; ++l) {
     if (p->level_h[l] <= 0 || p->level_w[l] <= 0) return GD4D_ERR_DIMS;
@@ -61,12 +69,14 @@ extern "C" {
 
 int gd4d_abi_version(void) { return GD4D_ABI_VERSION; }
 
+int gd4d_params_size(void) { return static_cast<int>(sizeof(gd4d_xview_params)); }
+
 const char* gd4d_strerror(int status) {
   switch (status) {
     case GD4D_OK: return "ok";
     case GD4D_ERR_NULL: return "required pointer is NULL";
     case GD4D_ERR_DIMS: return "bad or inconsistent dimension";
-    case GD4D_ERR_HEAD_DIM: return "unsupported head width (C/Hh must be 32)";
+    case GD4D_ERR_HEAD_DIM: return "unsupported channel width (narrow: C/Hh must be 32; wide: C*elem must be 512 or 1024 bytes)";
     case GD4D_ERR_ALIGN: return "pointer not 16-byte aligned";
     case GD4D_ERR_UNSUPPORTED: return "unsupported mode / dtype / size";
     case GD4D_ERR_CUDA: return "CUDA launch failed";

@@ -1,17 +1,19 @@
 // Backward of the fused cross-view sampling kernel.
 //
 // Same decomposition as the forward (one warp per (b, q, head); lane groups own
-// (valid candidate, level) items).  Nothing from the forward is saved: the
-// projection, mask and softmax are recomputed in registers (cheap), the four
-// corner slices are re-gathered, and per item the group forms three channel
-// dot-products with grad_out -- (s.g), (ds/dix.g), (ds/diy.g) -- by shuffle
-// reduction.  From those:
-//   grad_value        128-byte (fp32 grads) vector reductions `red.global.add.v4.f32`
-//                     straight into the channel-last grad map: one warp-wide
-//                     instruction retires 4 full corner slices
+// (valid candidate, level) items; narrow / wide lane layouts as in xview_fwd.cu).
+// Nothing from the forward is saved: the projection, mask and softmax are
+// recomputed in registers (cheap), the four corner runs are re-gathered, and per
+// item the group forms three channel dot-products with grad_out -- (s.g),
+// (ds/dix.g), (ds/diy.g) -- by shuffle reduction.  From those:
+//   grad_value        16-byte-per-lane vector reductions `red.global.add.v4.f32`
+//                     straight into the channel-last fp32 grad map: one warp-wide
+//                     instruction retires 512 contiguous bytes per corner run
 //   grad_attn_logits  softmax backward per head (C) / sigmoid' (A)
 //   grad_cam_logits   sigmoid' * sum_heads(partial_out . g)            (C)
 //   grad_offsets/ref  chain through u=(cx/den)/W_img ... lidar2img^T   
+// In wide mode the value-bias term rides along as one extra "all-ones" channel
+// whose gradient is grad_wsum.
 //
 // Reference being replaced: autograd through detr3d_transformer.py:376-438 /
 // deform3d_cross_attn.py:211-324, i.e. aten grid_sampler_2d_backward and mmcv
@@ -25,6 +27,12 @@ struct __align__(16) CandB {
   float u, v, den, w;   // w = sigmoid(cam logit) (C) or 1 (A)
   int np;               // n<<8 | p
   float du, dv, cg;     // accumulators: dL/du, dL/dv, sum_l sm[l,p]*(s.g)
+  __device__ __forceinline__ static CandB make(const Projected& pr, int n, int pi, float wc) {
+    CandB c;
+    c.u = pr.u; c.v = pr.v; c.den = pr.den; c.w = wc; c.np = (n << 8) | pi;
+    c.du = c.dv = c.cg = 0.f;
+    return c;
+  }
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -33,21 +41,18 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-template <int VEC>
-__device__ __forceinline__ void red_slice(float* addr, float w, const float (&g)[VEC]) {
-#pragma unroll
-  for (int i = 0; i < VEC; i += 4) red_add_v4(addr + i, w * g[i], w * g[i + 1], w * g[i + 2], w * g[i + 3]);
-}
-
-template <int MODE, typename VT>
+template <int MODE, typename VT, int LANES, int NV>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap) {
   constexpr int VEC = Slice<VT>::VEC;
-  constexpr int LANES = Slice<VT>::LANES;
+  constexpr int PL = VEC * NV;
   constexpr int GROUPS = 32 / LANES;
+  constexpr bool WIDE = (LANES == 32);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
+  WarpCtx w;
+  if (!warp_ctx(p, w)) return;
+  const int lane = w.lane;
   const int warp = threadIdx.x >> 5;
   const int grp = lane / LANES;
   const int sub = lane % LANES;
@@ -56,83 +61,31 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
   float* gsum = sw + kMaxLP;                                           // sum_n wcam*(s.g) per (l,p)
   float* doff = gsum + kMaxLP;                                         // dL/d offset (p,3)
   CandB* cands = reinterpret_cast<CandB*>(doff + 3 * kMaxLP);
-
-  const long long gw = static_cast<long long>(blockIdx.x) * kWarpsPerCta + warp;
-  const long long total_warps = static_cast<long long>(p.B) * p.Q * p.Hh;
-  if (gw >= total_warps) return;
-  const int h = static_cast<int>(gw % p.Hh);
-  const int bq = static_cast<int>(gw / p.Hh);
-  const int b = bq / p.Q;
-  const int q = bq - b * p.Q;
   const int LP = p.L * p.P;
 
-  const float* rp = p.ref + static_cast<size_t>(bq) * 3;
-  const float X0 = __fadd_rn(__fmul_rn(__ldg(rp + 0), p.pc_span[0]), p.pc_lo[0]);
-  const float Y0 = __fadd_rn(__fmul_rn(__ldg(rp + 1), p.pc_span[1]), p.pc_lo[1]);
-  const float Z0 = __fadd_rn(__fmul_rn(__ldg(rp + 2), p.pc_span[2]), p.pc_lo[2]);
-
-  // grad_out slice owned by this lane (identical in every lane group)
-  float g[VEC];
+  // grad_out run owned by this lane (identical in every lane group)
+  float g[PL];
   {
-    const float* go = p.grad_out + static_cast<size_t>(bq) * p.C + h * kHeadDim + sub * VEC;
+    const float* go = WIDE ? p.grad_out + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.C
+                           : p.grad_out + static_cast<size_t>(w.bq) * p.C + w.h * kHeadDim;
 #pragma unroll
-    for (int i = 0; i < VEC; i += 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(go + i));
-      g[i] = t.x; g[i + 1] = t.y; g[i + 2] = t.z; g[i + 3] = t.w;
-    }
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(go + (j * LANES + sub) * VEC + i));
+        g[j * VEC + i] = t.x; g[j * VEC + i + 1] = t.y; g[j * VEC + i + 2] = t.z; g[j * VEC + i + 3] = t.w;
+      }
   }
+  const float gws = (WIDE && p.grad_wsum != nullptr)
+                        ? __ldg(p.grad_wsum + static_cast<size_t>(w.bq) * p.Hh + w.h) : 0.f;
 
   if (MODE == GD4D_MODE_C) {
-    const float* a = p.attn_logits + (static_cast<size_t>(bq) * p.Hh + h) * LP;
-    const float x0 = lane < LP ? __ldg(a + lane) : -INFINITY;
-    const float x1 = lane + 32 < LP ? __ldg(a + lane + 32) : -INFINITY;
-    float m = fmaxf(x0, x1);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const float e0 = lane < LP ? expf(x0 - m) : 0.f;
-    const float e1 = lane + 32 < LP ? expf(x1 - m) : 0.f;
-    float s = e0 + e1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    sw[lane] = e0 / s;
-    sw[lane + 32] = e1 / s;
+    head_softmax(p, w, sw);
     gsum[lane] = 0.f;
     gsum[lane + 32] = 0.f;
     for (int i = lane; i < 3 * kMaxLP; i += 32) doff[i] = 0.f;
   }
-
-  // ---- phase 1: candidates ---------------------------------------------------------
-  const int PP = (MODE == GD4D_MODE_C) ? p.P : 1;
-  const int ncand = p.N * PP;
-  int nvalid = 0;
-  for (int c0 = 0; c0 < ncand; c0 += 32) {
-    const int c = c0 + lane;
-    bool valid = false;
-    CandB cd;
-    cd.u = cd.v = 0.f; cd.den = 1.f; cd.w = 1.f; cd.np = 0; cd.du = cd.dv = cd.cg = 0.f;
-    if (c < ncand) {
-      const int n = c / PP;
-      const int pi = c - n * PP;
-      float X = X0, Y = Y0, Z = Z0;
-      if (MODE == GD4D_MODE_C) {
-        const float* o = p.offsets + ((static_cast<size_t>(bq) * p.Hh + h) * p.P + pi) * 3;
-        X = __fadd_rn(X, __ldg(o + 0));
-        Y = __fadd_rn(Y, __ldg(o + 1));
-        Z = __fadd_rn(Z, __ldg(o + 2));
-      }
-      const float* M = p.lidar2img + (static_cast<size_t>(b) * p.N + n) * 16;
-      const Projected pr = project_point(M, X, Y, Z, p.img_w, p.img_h);
-      valid = pr.depth_ok & in_image<MODE>(pr.u, pr.v);
-      cd.u = pr.u; cd.v = pr.v; cd.den = pr.den; cd.np = (n << 8) | pi;
-      if (valid && MODE == GD4D_MODE_C)
-        cd.w = sigmoidf_(__ldg(p.cam_logits + static_cast<size_t>(b) * p.N * p.Q +
-                               static_cast<size_t>(n) * p.Q + q));
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, valid);
-    if (valid) cands[nvalid + __popc(bal & ((1u << lane) - 1u))] = cd;
-    nvalid += __popc(bal);
-  }
-  __syncwarp();
+  const int nvalid = build_candidates<MODE, CandB>(p, w, cands, false);
 
   // ---- phase 2: re-gather, dot with grad_out, scatter feature gradients ---------------------
   const int total = nvalid * p.L;
@@ -152,7 +105,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
       smw = sw[l * p.P + pi];
       wt = smw * cw;
     } else {
-      alog = p.attn_logits + ((static_cast<size_t>(b) * p.Q + q) * p.N + n) * p.P * p.L + l;
+      alog = p.attn_logits + (static_cast<size_t>(w.bq) * p.N + n) * p.P * p.L + l;
       wt = 0.f;
       for (int pp = 0; pp < p.P; ++pp) wt += sigmoidf_(__ldg(alog + pp * p.L));
     }
@@ -162,30 +115,44 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     const float iy = to_pixel(to_grid<MODE>(cv), static_cast<float>(H));
     const Footprint f = footprint(ix, iy, W, H);
     const VT* base = static_cast<const VT*>(p.value[l]);
-    const size_t img = static_cast<size_t>(b) * p.N + n;
-    const size_t e00 = ((img * H + f.y0) * W + f.x0) * p.C + static_cast<size_t>(h) * kHeadDim + sub * VEC;
+    const size_t img = static_cast<size_t>(w.b) * p.N + n;
+    const size_t e00 = ((img * H + f.y0) * W + f.x0) * p.C +
+                       (WIDE ? 0 : static_cast<size_t>(w.h) * kHeadDim) + sub * VEC;
     const size_t rowst = static_cast<size_t>(W) * p.C;
-    float c00[VEC], c01[VEC], c10[VEC], c11[VEC];
+    float c00[PL], c01[PL], c10[PL], c11[PL];
     const bool a00 = active & f.in00, a01 = active & f.in01, a10 = active & f.in10, a11 = active & f.in11;
-    Slice<VT>::load(base + e00, a00, c00);
-    Slice<VT>::load(base + e00 + p.C, a01, c01);
-    Slice<VT>::load(base + e00 + rowst, a10, c10);
-    Slice<VT>::load(base + e00 + rowst + p.C, a11, c11);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int o = j * LANES * VEC;
+      Slice<VT>::load(base + e00 + o, a00, *reinterpret_cast<float(*)[VEC]>(&c00[j * VEC]));
+      Slice<VT>::load(base + e00 + p.C + o, a01, *reinterpret_cast<float(*)[VEC]>(&c01[j * VEC]));
+      Slice<VT>::load(base + e00 + rowst + o, a10, *reinterpret_cast<float(*)[VEC]>(&c10[j * VEC]));
+      Slice<VT>::load(base + e00 + rowst + p.C + o, a11, *reinterpret_cast<float(*)[VEC]>(&c11[j * VEC]));
+    }
     const float w00 = (1.f - f.tx) * (1.f - f.ty), w01 = f.tx * (1.f - f.ty);
     const float w10 = (1.f - f.tx) * f.ty, w11 = f.tx * f.ty;
 
     // feature-map gradient: dL/df_c += wt * w_c * g   (vector reductions, no return value)
     float* gv = p.grad_value[l];
     if (gv != nullptr && wt != 0.f) {
-      if (a00) red_slice<VEC>(gv + e00, wt * w00, g);
-      if (a01) red_slice<VEC>(gv + e00 + p.C, wt * w01, g);
-      if (a10) red_slice<VEC>(gv + e00 + rowst, wt * w10, g);
-      if (a11) red_slice<VEC>(gv + e00 + rowst + p.C, wt * w11, g);
+      const float s00 = wt * w00, s01 = wt * w01, s10 = wt * w10, s11 = wt * w11;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+          const int o = j * LANES * VEC + i;
+          const float g0 = g[j * VEC + i], g1 = g[j * VEC + i + 1], g2 = g[j * VEC + i + 2],
+                      g3 = g[j * VEC + i + 3];
+          if (a00) red_add_v4(gv + e00 + o, s00 * g0, s00 * g1, s00 * g2, s00 * g3);
+          if (a01) red_add_v4(gv + e00 + p.C + o, s01 * g0, s01 * g1, s01 * g2, s01 * g3);
+          if (a10) red_add_v4(gv + e00 + rowst + o, s10 * g0, s10 * g1, s10 * g2, s10 * g3);
+          if (a11) red_add_v4(gv + e00 + rowst + p.C + o, s11 * g0, s11 * g1, s11 * g2, s11 * g3);
+        }
     }
 
     float sdot = 0.f, dxdot = 0.f, dydot = 0.f;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
+    for (int i = 0; i < PL; ++i) {
       sdot += g[i] * (w00 * c00[i] + w01 * c01[i] + w10 * c10[i] + w11 * c11[i]);
       dxdot += g[i] * ((c01[i] - c00[i]) * (1.f - f.ty) + (c11[i] - c10[i]) * f.ty);
       dydot += g[i] * ((c10[i] - c00[i]) * (1.f - f.tx) + (c11[i] - c01[i]) * f.tx);
@@ -195,6 +162,13 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
       sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
       dxdot += __shfl_xor_sync(0xffffffffu, dxdot, o);
       dydot += __shfl_xor_sync(0xffffffffu, dydot, o);
+    }
+    if (WIDE) {  // the bias rides as an all-ones channel: 1 inside the map, 0 outside
+      const float i00 = f.in00 ? 1.f : 0.f, i01 = f.in01 ? 1.f : 0.f, i10 = f.in10 ? 1.f : 0.f,
+                  i11 = f.in11 ? 1.f : 0.f;
+      sdot += gws * (w00 * i00 + w01 * i01 + w10 * i10 + w11 * i11);
+      dxdot += gws * ((i01 - i00) * (1.f - f.ty) + (i11 - i10) * f.ty);
+      dydot += gws * ((i10 - i00) * (1.f - f.tx) + (i11 - i01) * f.tx);
     }
     if (active && sub == 0) {
       atomicAdd(&cands[k].du, wt * static_cast<float>(W) * dxdot);
@@ -221,7 +195,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     float dot = s0 * g0 + s1 * g1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    float* ga = p.grad_attn_logits + (static_cast<size_t>(bq) * p.Hh + h) * LP;
+    float* ga = p.grad_attn_logits + (static_cast<size_t>(w.bq) * p.Hh + w.h) * LP;
     if (lane < LP) atomicAdd(ga + lane, s0 * (g0 - dot));
     if (lane + 32 < LP) atomicAdd(ga + lane + 32, s1 * (g1 - dot));
   }
@@ -231,7 +205,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     const CandB cd = cands[k];
     const int n = cd.np >> 8;
     const int pi = cd.np & 0xff;
-    const float* M = p.lidar2img + (static_cast<size_t>(b) * p.N + n) * 16;
+    const float* M = p.lidar2img + (static_cast<size_t>(w.b) * p.N + n) * 16;
     const float dcx = cd.du / (cd.den * p.img_w);
     const float dcy = cd.dv / (cd.den * p.img_h);
     const float dcz = -(cd.du * cd.u + cd.dv * cd.v) / cd.den;  // valid => cz > eps => d den/d cz = 1
@@ -244,7 +218,8 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
       atomicAdd(&doff[pi * 3 + 1], dY);
       atomicAdd(&doff[pi * 3 + 2], dZ);
       if (p.grad_cam_logits != nullptr)
-        atomicAdd(p.grad_cam_logits + static_cast<size_t>(b) * p.N * p.Q + static_cast<size_t>(n) * p.Q + q,
+        atomicAdd(p.grad_cam_logits + static_cast<size_t>(w.b) * p.N * p.Q +
+                      static_cast<size_t>(n) * p.Q + w.q,
                   cd.w * (1.f - cd.w) * cd.cg);
     }
   }
@@ -256,7 +231,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
       rZ += __shfl_xor_sync(0xffffffffu, rZ, o);
     }
     if (lane == 0 && nvalid > 0) {
-      float* gr = p.grad_ref + static_cast<size_t>(bq) * 3;
+      float* gr = p.grad_ref + static_cast<size_t>(w.bq) * 3;
       atomicAdd(gr + 0, rX * p.pc_span[0]);
       atomicAdd(gr + 1, rY * p.pc_span[1]);
       atomicAdd(gr + 2, rZ * p.pc_span[2]);
@@ -264,14 +239,14 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
   }
   if (MODE == GD4D_MODE_C && p.grad_offsets != nullptr) {
     __syncwarp();
-    float* go = p.grad_offsets + (static_cast<size_t>(bq) * p.Hh + h) * p.P * 3;
+    float* go = p.grad_offsets + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.P * 3;
     for (int i = lane; i < p.P * 3; i += 32) atomicAdd(go + i, doff[i]);
   }
 }
 
-template <int MODE, typename VT>
+template <int MODE, typename VT, int LANES, int NV>
 static int launch_bwd(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream) {
-  auto kern = xview_bwd_kernel<MODE, VT>;
+  auto kern = xview_bwd_kernel<MODE, VT, LANES, NV>;
   if (g.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem);
     if (e != cudaSuccess) return GD4D_ERR_CUDA;
@@ -282,16 +257,21 @@ static int launch_bwd(const gd4d_xview_params& p, const LaunchGeom& g, cudaStrea
 
 int dispatch_backward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream) {
   const bool bf16 = p.value_dtype == GD4D_BF16;
-  switch (p.mode) {
-    case GD4D_MODE_A:
-      return bf16 ? launch_bwd<GD4D_MODE_A, __nv_bfloat16>(p, g, stream)
-                  : launch_bwd<GD4D_MODE_A, float>(p, g, stream);
-    case GD4D_MODE_C:
-      return bf16 ? launch_bwd<GD4D_MODE_C, __nv_bfloat16>(p, g, stream)
-                  : launch_bwd<GD4D_MODE_C, float>(p, g, stream);
-    default:
-      return GD4D_ERR_UNSUPPORTED;
+  if (p.mode == GD4D_MODE_A) {
+    return bf16 ? launch_bwd<GD4D_MODE_A, __nv_bfloat16, 4, 1>(p, g, stream)
+                : launch_bwd<GD4D_MODE_A, float, 8, 1>(p, g, stream);
   }
+  if (p.mode == GD4D_MODE_C && !p.wide) {
+    return bf16 ? launch_bwd<GD4D_MODE_C, __nv_bfloat16, 4, 1>(p, g, stream)
+                : launch_bwd<GD4D_MODE_C, float, 8, 1>(p, g, stream);
+  }
+  if (p.mode == GD4D_MODE_C && p.wide) {
+    if (bf16) return g.nv == 1 ? launch_bwd<GD4D_MODE_C, __nv_bfloat16, 32, 1>(p, g, stream)
+                               : launch_bwd<GD4D_MODE_C, __nv_bfloat16, 32, 2>(p, g, stream);
+    return g.nv == 1 ? launch_bwd<GD4D_MODE_C, float, 32, 1>(p, g, stream)
+                     : launch_bwd<GD4D_MODE_C, float, 32, 2>(p, g, stream);
+  }
+  return GD4D_ERR_UNSUPPORTED;
 }
 
 }  // namespace gd4d

@@ -83,7 +83,6 @@ struct Slice;  // VEC = channels per 16-byte lane load
 template <>
 struct Slice<float> {
   static constexpr int VEC = 4;
-  static constexpr int LANES = kHeadDim / VEC;  // 8 lanes cover one 128-byte head slice
   __device__ __forceinline__ static void load(const float* p, bool pred, float (&v)[VEC]) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (pred) t = __ldg(reinterpret_cast<const float4*>(p));
@@ -94,7 +93,6 @@ struct Slice<float> {
 template <>
 struct Slice<__nv_bfloat16> {
   static constexpr int VEC = 8;
-  static constexpr int LANES = kHeadDim / VEC;  // 4 lanes cover one 64-byte head slice
   __device__ __forceinline__ static void load(const __nv_bfloat16* p, bool pred, float (&v)[VEC]) {
     uint4 t = make_uint4(0u, 0u, 0u, 0u);
     if (pred) t = __ldg(reinterpret_cast<const uint4*>(p));
@@ -128,6 +126,96 @@ __device__ __forceinline__ Footprint footprint(float ix, float iy, int W, int H)
 
 struct LaunchGeom {
   int grid, block, smem, cand_cap;
+  int nv;  // wide mode: 16-byte vectors per lane per corner (C*elem/512), else 1
 };
+
+// Per-warp work coordinates
+struct WarpCtx {
+  int b, q, h, bq, lane;
+  float X0, Y0, Z0;  // reference point in metres
+};
+
+__device__ __forceinline__ bool warp_ctx(const gd4d_xview_params& p, WarpCtx& w) {
+  const int warp = threadIdx.x >> 5;
+  const long long gw = static_cast<long long>(blockIdx.x) * kWarpsPerCta + warp;
+  const long long total_warps = static_cast<long long>(p.B) * p.Q * p.Hh;
+  if (gw >= total_warps) return false;
+  w.lane = threadIdx.x & 31;
+  w.h = static_cast<int>(gw % p.Hh);
+  w.bq = static_cast<int>(gw / p.Hh);
+  w.b = w.bq / p.Q;
+  w.q = w.bq - w.b * p.Q;
+  const float* rp = p.ref + static_cast<size_t>(w.bq) * 3;
+  w.X0 = __fadd_rn(__fmul_rn(__ldg(rp + 0), p.pc_span[0]), p.pc_lo[0]);
+  w.Y0 = __fadd_rn(__fmul_rn(__ldg(rp + 1), p.pc_span[1]), p.pc_lo[1]);
+  w.Z0 = __fadd_rn(__fmul_rn(__ldg(rp + 2), p.pc_span[2]), p.pc_lo[2]);
+  return true;
+}
+
+// softmax over the head's L*P (<= 64) logits into sw[0..64) (zeros past L*P)
+__device__ __forceinline__ void head_softmax(const gd4d_xview_params& p, const WarpCtx& w, float* sw) {
+  const int LP = p.L * p.P;
+  const int lane = w.lane;
+  const float* a = p.attn_logits + (static_cast<size_t>(w.bq) * p.Hh + w.h) * LP;
+  const float x0 = lane < LP ? __ldg(a + lane) : -INFINITY;
+  const float x1 = lane + 32 < LP ? __ldg(a + lane + 32) : -INFINITY;
+  float m = fmaxf(x0, x1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float e0 = lane < LP ? expf(x0 - m) : 0.f;
+  const float e1 = lane + 32 < LP ? expf(x1 - m) : 0.f;
+  float s = e0 + e1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  sw[lane] = e0 / s;
+  sw[lane + 32] = e1 / s;
+}
+
+// Phase 1 of both kernels: the 32 lanes project the warp's N*P candidate points in
+// parallel and ballot-compact the valid ones into `cands` (shared memory).
+// CandT must provide:  static CandT make(const Projected&, int n, int pi, float wc).
+template <int MODE, typename CandT>
+__device__ __forceinline__ int build_candidates(const gd4d_xview_params& p, const WarpCtx& w,
+                                                CandT* cands, bool write_mask) {
+  const int PP = (MODE == GD4D_MODE_C) ? p.P : 1;  // mode A: one centre point per camera
+  const int ncand = p.N * PP;
+  int nvalid = 0;
+  for (int c0 = 0; c0 < ncand; c0 += 32) {
+    const int c = c0 + w.lane;
+    bool valid = false;
+    Projected pr;
+    pr.u = pr.v = pr.cx = pr.cy = 0.f; pr.den = 1.f; pr.depth_ok = false;
+    float wc = 1.f;
+    int n = 0, pi = 0;
+    if (c < ncand) {
+      n = c / PP;
+      pi = c - n * PP;
+      float X = w.X0, Y = w.Y0, Z = w.Z0;
+      if (MODE == GD4D_MODE_C) {
+        const float* o = p.offsets + ((static_cast<size_t>(w.bq) * p.Hh + w.h) * p.P + pi) * 3;
+        X = __fadd_rn(X, __ldg(o + 0));
+        Y = __fadd_rn(Y, __ldg(o + 1));
+        Z = __fadd_rn(Z, __ldg(o + 2));
+      }
+      const float* M = p.lidar2img + (static_cast<size_t>(w.b) * p.N + n) * 16;
+      pr = project_point(M, X, Y, Z, p.img_w, p.img_h);
+      valid = pr.depth_ok & in_image<MODE>(pr.u, pr.v);
+      if (write_mask) {
+        if (MODE == GD4D_MODE_C)
+          p.mask[(((static_cast<size_t>(w.b) * p.N + n) * p.Q + w.q) * p.Hh + w.h) * p.P + pi] = valid;
+        else if (w.h == 0)
+          p.mask[static_cast<size_t>(w.bq) * p.N + n] = valid;
+      }
+      if (valid && MODE == GD4D_MODE_C)  // reference views (B,Q,N) memory as (B,N,Q): flat[n*Q+q]
+        wc = sigmoidf_(__ldg(p.cam_logits + static_cast<size_t>(w.b) * p.N * p.Q +
+                             static_cast<size_t>(n) * p.Q + w.q));
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if (valid) cands[nvalid + __popc(bal & ((1u << w.lane) - 1u))] = CandT::make(pr, n, pi, wc);
+    nvalid += __popc(bal);
+  }
+  __syncwarp();
+  return nvalid;
+}
 
 }  // namespace gd4d

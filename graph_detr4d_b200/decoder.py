@@ -1,0 +1,136 @@
+"""Caller of the hot path: a thin re-statement of the reference's decoder loop
+(SURVEY.md section 8a row a9), needed to run BASELINE.json configs 2-3.
+
+  Detr3DTransformerDecoder.forward   detr3d_transformer.py:166-225
+      6 x layer(query, key=None, value=mlvl_feats, query_pos, reference_points, img_metas)
+      then ref[..., :2] += reg[..., :2]; ref[..., 2] += reg[..., 4] in logit space,
+      sigmoid, DETACH (:201-214)
+  Detr3DTransformer.forward          detr3d_transformer.py:128-147
+      split query_embed -> (query_pos, query); ref = sigmoid(Linear(query_pos))
+
+The layer itself is mmcv's DetrTransformerDecoderLayer with
+operation_order ('self_attn','norm','cross_attn','norm','ffn','norm')
+(projects/configs/detr3d/detr3d_res50.py:65-83): post-norm, nn.MultiheadAttention
+with q = k = query + query_pos, FFN 256->512->256.  Sub-module names follow mmcv's
+(`attentions.{0,1}`, `ffns.0.layers`, `norms.{0,1,2}`) so decoder checkpoints map
+1:1.  Everything except the cross-attention is stock torch (cuBLAS / library) --
+plumbing around the hot path, deliberately not re-implemented.
+
+``cross_attn_factory`` lets the CPU baseline (bench.py --impl reference) build the
+very same decoder around the oracle's port of the attention.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .modules import build_attention, inverse_sigmoid
+
+
+class SelfAttention(nn.Module):
+    """mmcv.cnn.bricks.transformer.MultiheadAttention, batch_first=False."""
+
+    def __init__(self, embed_dims=256, num_heads=8, dropout=0.1):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, dropout)
+        self.dropout_layer = nn.Dropout(dropout)
+
+    def forward(self, query, query_pos=None):
+        identity = query
+        q = k = query if query_pos is None else query + query_pos
+        out = self.attn(q, k, value=query, need_weights=False)[0]
+        return identity + self.dropout_layer(out)
+
+
+class FFN(nn.Module):
+    """mmcv FFN: Linear-ReLU-Dropout-Linear-Dropout + identity."""
+
+    def __init__(self, embed_dims=256, feedforward_channels=512, ffn_drop=0.1):
+        super().__init__()
+        self.layers = nn.Sequential(
+            nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True), nn.Dropout(ffn_drop)),
+            nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
+
+    def forward(self, x):
+        return x + self.layers(x)
+
+
+class DecoderLayer(nn.Module):
+    def __init__(self, cross_attn: nn.Module, embed_dims=256, num_heads=8, feedforward_channels=512,
+                 dropout=0.1):
+        super().__init__()
+        self.attentions = nn.ModuleList([SelfAttention(embed_dims, num_heads, dropout), cross_attn])
+        self.ffns = nn.ModuleList([FFN(embed_dims, feedforward_channels, dropout)])
+        self.norms = nn.ModuleList([nn.LayerNorm(embed_dims) for _ in range(3)])
+
+    def forward(self, query, value, query_pos, reference_points, img_metas):
+        query = self.norms[0](self.attentions[0](query, query_pos))
+        query = self.attentions[1](query, None, value, None, query_pos=query_pos,
+                                   reference_points=reference_points, img_metas=img_metas)
+        query = self.norms[1](query)
+        return self.norms[2](self.ffns[0](query))
+
+
+class Detr3DTransformerDecoder(nn.Module):
+    def __init__(self, attn_cfg: dict, num_layers=6, embed_dims=256, num_heads=8,
+                 feedforward_channels=512, dropout=0.1, return_intermediate=True,
+                 cross_attn_factory: Optional[Callable[[dict], nn.Module]] = None):
+        super().__init__()
+        factory = cross_attn_factory or build_attention
+        self.layers = nn.ModuleList([
+            DecoderLayer(factory(dict(attn_cfg)), embed_dims, num_heads, feedforward_channels, dropout)
+            for _ in range(num_layers)])
+        self.return_intermediate = return_intermediate
+        self.embed_dims = embed_dims
+
+    def forward(self, query, value, query_pos, reference_points, reg_branches=None, img_metas=None):
+        output = query
+        intermediate, intermediate_ref = [], []
+        for lid, layer in enumerate(self.layers):
+            output = layer(output, value, query_pos, reference_points, img_metas)
+            if reg_branches is not None:                                    # :201-214
+                tmp = reg_branches[lid](output.permute(1, 0, 2))
+                new_ref = torch.zeros_like(reference_points)
+                new_ref[..., :2] = tmp[..., :2] + inverse_sigmoid(reference_points[..., :2])
+                new_ref[..., 2:3] = tmp[..., 4:5] + inverse_sigmoid(reference_points[..., 2:3])
+                reference_points = new_ref.sigmoid().detach()
+            if self.return_intermediate:
+                intermediate.append(output)
+                intermediate_ref.append(reference_points)
+        if self.return_intermediate:
+            return torch.stack(intermediate), torch.stack(intermediate_ref)
+        return output, reference_points
+
+
+class Detr3DTransformer(nn.Module):
+    """query_embed -> (query_pos, query); initial reference points; decoder."""
+
+    def __init__(self, decoder: Detr3DTransformerDecoder, num_query=900, code_size=10, num_reg_fcs=2):
+        super().__init__()
+        self.decoder = decoder
+        self.embed_dims = decoder.embed_dims
+        self.reference_points = nn.Linear(self.embed_dims, 3)
+        self.query_embedding = nn.Embedding(num_query, self.embed_dims * 2)   # detr3d_head.py:97-99
+        branches = []
+        for _ in range(len(decoder.layers)):                                # detr3d_head.py:72-95
+            fcs = []
+            for _ in range(num_reg_fcs):
+                fcs += [nn.Linear(self.embed_dims, self.embed_dims), nn.ReLU()]
+            fcs.append(nn.Linear(self.embed_dims, code_size))
+            branches.append(nn.Sequential(*fcs))
+        self.reg_branches = nn.ModuleList(branches)
+        nn.init.xavier_uniform_(self.reference_points.weight)
+        nn.init.constant_(self.reference_points.bias, 0.0)
+
+    def forward(self, mlvl_feats, img_metas, batch_size: int):
+        query_embed = self.query_embedding.weight
+        query_pos, query = torch.split(query_embed, self.embed_dims, dim=1)
+        query_pos = query_pos.unsqueeze(0).expand(batch_size, -1, -1)
+        query = query.unsqueeze(0).expand(batch_size, -1, -1)
+        reference_points = self.reference_points(query_pos).sigmoid()       # NOT detached in layer 0
+        inter_states, inter_refs = self.decoder(
+            query.permute(1, 0, 2), mlvl_feats, query_pos.permute(1, 0, 2), reference_points,
+            reg_branches=self.reg_branches, img_metas=img_metas)
+        return inter_states, reference_points, inter_refs

@@ -1,0 +1,93 @@
+"""CUDA-graph capture of the decoder training step.
+
+At batch 1 / 900 queries the decoder step is ~1100 tiny launches and the host
+(Python + autograd dispatch) cannot issue them as fast as a B200 retires them, so
+the whole step -- forward, backward (our fused kernels included: they are plain
+stream-ordered launches through the C ABI, hence capturable) and the optimizer --
+is captured once and replayed.  No tracing compiler is involved: capture records
+exactly the kernels eager mode launched.
+
+Data-parallel use (one process per GPU): gradients live in ONE flat fp32 buffer
+(every ``param.grad`` is a view of it), so the only collective of the step is a
+single NCCL all-reduce of that buffer between the captured forward/backward and
+the captured optimizer step (the sampling path itself needs no
+communication).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import modules
+
+
+class GraphedTrainStep:
+    def __init__(self, model: torch.nn.Module, forward_loss: Callable[[Sequence[torch.Tensor]], torch.Tensor],
+                 example_feats: Sequence[torch.Tensor], img_metas, lr=2e-4, weight_decay=0.01,
+                 warmup_iters: int = 3, feats_require_grad: bool = True, world_size: int = 1):
+        """``forward_loss(feats) -> scalar loss`` must only launch capturable work."""
+        self.model = model
+        self.world = world_size
+        dev = example_feats[0].device
+        self.device = dev
+        params = [p for p in model.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in params)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        o = 0
+        for p in params:
+            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.opt = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=True, capturable=True)
+        self.static_feats: List[torch.Tensor] = [
+            f.detach().clone().requires_grad_(feats_require_grad) for f in example_feats]
+        self.img_metas = img_metas
+        modules.lidar2img_device(img_metas, dev)           # upload once, outside capture
+        self._forward_loss = forward_loss
+
+        def fwd_bwd():
+            modules.clear_pack_cache()                     # the pack kernels must be part of the capture
+            self.flat_grad.zero_()
+            for f in self.static_feats:
+                f.grad = None
+            loss = forward_loss(self.static_feats)
+            loss.backward()
+            return loss.detach()
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup_iters):
+                fwd_bwd()
+                self._allreduce()
+                self.opt.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self.static_loss = fwd_bwd()
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt):
+            self.opt.step()
+        torch.cuda.synchronize(dev)
+
+    def _allreduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+
+    def set_inputs(self, feats: Optional[Sequence[torch.Tensor]] = None, img_metas=None):
+        """Stream-ordered refresh of the static inputs (H2D when ``feats`` are host tensors)."""
+        if img_metas is not None:
+            modules.lidar2img_device(img_metas, self.device)        # in-place update of the static buffer
+        if feats is not None:
+            with torch.no_grad():
+                for dst, src in zip(self.static_feats, feats):
+                    dst.copy_(src, non_blocking=True)
+
+    def step(self) -> torch.Tensor:
+        self.graph_fb.replay()
+        self._allreduce()
+        self.graph_opt.replay()
+        return self.static_loss

@@ -7,7 +7,7 @@ CPU / eager fallback: CPU tensors or a missing library raise.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -17,7 +17,19 @@ from . import _lib
 from ._lib import BF16, F32, MODE_A, MODE_C, MODE_V2, XViewParams
 
 __all__ = ["XViewConfig", "pack_features", "PackedFeatures", "xview_forward", "xview_backward",
-           "xview_attention", "lidar2img_to_tensor", "MODE_A", "MODE_C", "MODE_V2"]
+           "xview_attention", "lidar2img_to_tensor", "prepare_forward", "prepare_backward",
+           "launch_count", "MODE_A", "MODE_C", "MODE_V2"]
+
+_LAUNCHES = 0      # kernels of libgd4d_xview.so launched by this process (bench: gpu_launches)
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def _count(n: int = 1):
+    global _LAUNCHES
+    _LAUNCHES += n
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -50,53 +62,103 @@ def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
 # --------------------------------------------------------------------------------------
 # feature packing (NCHW -> channel-last), once per forward, shared by the 6 layers
 # --------------------------------------------------------------------------------------
-class _PackFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, feat: torch.Tensor, out_dtype: torch.dtype):
-        B, N, Cc, H, W = feat.shape
-        src = feat.contiguous()
-        dst = torch.empty((B * N, H, W, Cc), device=feat.device, dtype=out_dtype)
-        st = _lib.load().gd4d_pack_nchw(src.data_ptr(), dst.data_ptr(), _dtype_code(src),
-                                        _dtype_code(dst), B * N, Cc, H, W, _stream_ptr(feat.device))
-        _lib.check(st, "gd4d_pack_nchw")
-        ctx.shape = (B, N, Cc, H, W)
-        ctx.in_dtype = feat.dtype
-        return dst
-
-    @staticmethod
-    def backward(ctx, grad):
-        B, N, Cc, H, W = ctx.shape
-        # (B*N,H,W,C) -> a (B,N,C,H,W) VIEW with channels-last strides: no copy
-        g = grad.permute(0, 3, 1, 2).unflatten(0, (B, N))
-        if g.dtype != ctx.in_dtype:
-            g = g.to(ctx.in_dtype)
-        return g, None
-
-
-def pack_level(feat: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """(B,N,C,H,W) -> channel-last (B*N,H,W,C).  Zero-copy when the map already is
-    channels_last in memory (a backbone run in torch.channels_last hands us that)."""
-    _require_cuda(feat, "feature map")
-    if feat.dim() != 5:
-        raise ValueError(f"feature map must be (B,N,C,H,W), got {tuple(feat.shape)}")
-    dtype = dtype or feat.dtype
+def _pack_raw(feat: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """(B,N,C,H,W) -> detached channel-last (B*N,H,W,C); zero-copy when the map is
+    already channels_last in memory (a backbone run in torch.channels_last)."""
     B, N, Cc, H, W = feat.shape
+    feat = feat.detach()
     if dtype == feat.dtype:
         try:
             nhwc = feat.view(B * N, Cc, H, W).permute(0, 2, 3, 1)
         except RuntimeError:
             nhwc = None
         if nhwc is not None and nhwc.is_contiguous():
-            return nhwc  # already channel-last in memory
-    return _PackFn.apply(feat, dtype)
+            return nhwc
+    src = feat.contiguous()
+    dst = torch.empty((B * N, H, W, Cc), device=feat.device, dtype=dtype)
+    st = _lib.load().gd4d_pack_nchw(src.data_ptr(), dst.data_ptr(), _dtype_code(src), _dtype_code(dst),
+                                    B * N, Cc, H, W, _stream_ptr(feat.device))
+    _lib.check(st, "gd4d_pack_nchw")
+    _count()
+    return dst
+
+
+class _AttachFn(torch.autograd.Function):
+    """Differentiable alias of an already packed level (dense value_proj path): the
+    backward hands the channel-last gradient back as a (B,N,C,H,W) VIEW, no copy."""
+
+    @staticmethod
+    def forward(ctx, feat: torch.Tensor, packed: torch.Tensor):
+        ctx.shape = tuple(feat.shape)
+        ctx.in_dtype = feat.dtype
+        return packed.view_as(packed)
+
+    @staticmethod
+    def backward(ctx, grad):
+        B, N = ctx.shape[:2]
+        g = grad.permute(0, 3, 1, 2).unflatten(0, (B, N))
+        return (g if g.dtype == ctx.in_dtype else g.to(ctx.in_dtype)), None
+
+
+class GradSink:
+    """ONE fp32 channel-last gradient map per level, shared by every decoder layer of
+    a forward: each layer's backward kernel accumulates into it with vector
+    atomics, so the dense zero-fill and the dense read-modify-write happen once per
+    step instead of once per layer (bytes_bwd)."""
+
+    def __init__(self, levels: Sequence[torch.Tensor]):
+        self._shapes = [tuple(v.shape) for v in levels]
+        self._device = levels[0].device
+        self.buffers: Optional[List[torch.Tensor]] = None
+
+    def get(self) -> List[torch.Tensor]:
+        if self.buffers is None:
+            # one allocation, one memset for all levels
+            sizes = [int(np.prod(s)) for s in self._shapes]
+            flat = torch.zeros(sum(sizes), device=self._device, dtype=torch.float32)
+            self.buffers, o = [], 0
+            for s, n in zip(self._shapes, sizes):
+                self.buffers.append(flat[o:o + n].view(s))
+                o += n
+        return self.buffers
+
+    def take(self):
+        b, self.buffers = self.buffers, None
+        return b
+
+
+class _SinkFn(torch.autograd.Function):
+    """Graph node that owns the GradSink: its `token` output is an input of every
+    layer's sampling op, so autograd runs this backward only after ALL layers have
+    accumulated; it then returns the shared maps as (B,N,C,H,W) views."""
+
+    @staticmethod
+    def forward(ctx, sink: GradSink, *feats: torch.Tensor):
+        ctx.sink = sink
+        ctx.meta = [(tuple(f.shape), f.dtype) for f in feats]
+        return feats[0].new_zeros(())
+
+    @staticmethod
+    def backward(ctx, _gtoken):
+        bufs = ctx.sink.take()
+        if bufs is None:
+            return (None,) + (None,) * len(ctx.meta)
+        outs = []
+        for buf, (shape, dtype) in zip(bufs, ctx.meta):
+            g = buf.permute(0, 3, 1, 2).unflatten(0, shape[:2])
+            outs.append(g if g.dtype == dtype else g.to(dtype))
+        return (None, *outs)
 
 
 @dataclass
 class PackedFeatures:
     """Channel-last feature maps of one forward, plus the batch/camera split."""
-    levels: List[torch.Tensor]            # each (B*N, H_l, W_l, C)
+    levels: List[torch.Tensor]            # detached, each (B*N, H_l, W_l, C)
     B: int
     N: int
+    token: Optional[torch.Tensor] = None  # autograd handle of the shared GradSink
+    sink: Optional[GradSink] = None
+    sources: Optional[List[torch.Tensor]] = field(default=None, repr=False)
 
     @property
     def C(self) -> int:
@@ -106,12 +168,30 @@ class PackedFeatures:
     def shapes(self) -> List[Tuple[int, int]]:
         return [(int(v.shape[1]), int(v.shape[2])) for v in self.levels]
 
+    def differentiable_levels(self) -> List[torch.Tensor]:
+        """Packed levels as autograd-connected tensors (dense value_proj path)."""
+        if self.sources is None:
+            return self.levels
+        return [_AttachFn.apply(f, v) if f.requires_grad else v for f, v in zip(self.sources, self.levels)]
+
+
+def pack_level(feat: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    _require_cuda(feat, "feature map")
+    if feat.dim() != 5:
+        raise ValueError(f"feature map must be (B,N,C,H,W), got {tuple(feat.shape)}")
+    return _pack_raw(feat, dtype or feat.dtype)
+
 
 def pack_features(mlvl_feats: Sequence[torch.Tensor], dtype: Optional[torch.dtype] = None) -> PackedFeatures:
     """Pack the reference's ``value`` (python list of (B,N,C,H,W) maps,
     detr3d_transformer.py:142-143) once; all decoder layers then share it."""
     B, N = int(mlvl_feats[0].shape[0]), int(mlvl_feats[0].shape[1])
-    return PackedFeatures([pack_level(f, dtype) for f in mlvl_feats], B, N)
+    levels = [pack_level(f, dtype) for f in mlvl_feats]
+    token = sink = None
+    if torch.is_grad_enabled() and any(f.requires_grad for f in mlvl_feats):
+        sink = GradSink(levels)
+        token = _SinkFn.apply(sink, *mlvl_feats)
+    return PackedFeatures(levels, B, N, token, sink, list(mlvl_feats))
 
 
 def lidar2img_to_tensor(img_metas, device) -> torch.Tensor:
@@ -133,6 +213,7 @@ class XViewConfig:
     pc_range: Tuple[float, ...]
     img_h: float
     img_w: float
+    wide: bool = False          # mode C: gather-then-project (include/gd4d_xview.h)
 
 
 def _fill_params(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
@@ -144,6 +225,7 @@ def _fill_params(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: in
     p = XViewParams()
     p.abi_version = _lib.ABI_VERSION
     p.mode = cfg.mode
+    p.wide = 1 if cfg.wide else 0
     p.value_dtype = _dtype_code(values[0])
     p.B, p.Q, p.N = B, int(ref.shape[1]), N
     p.Hh = cfg.num_heads if cfg.mode != MODE_A else Cc // 32
@@ -168,7 +250,7 @@ def _fill_params(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: in
     return p
 
 
-def _check_shapes(cfg, B, N, L, Cc, ref, attn_logits, offsets, cam_logits, lidar2img):
+def _check_shapes(cfg, B, N, L, ref, attn_logits, offsets, cam_logits, lidar2img):
     Q = ref.shape[1]
     if tuple(ref.shape) != (B, Q, 3):
         raise ValueError(f"reference_points must be (B,Q,3), got {tuple(ref.shape)}")
@@ -187,9 +269,14 @@ def _check_shapes(cfg, B, N, L, Cc, ref, attn_logits, offsets, cam_logits, lidar
         raise ValueError(f"attn_logits holds {attn_logits.numel()} values, expected {want}")
 
 
+def _out_shape(cfg, B, Q, Cc):
+    return (B, Q, cfg.num_heads, Cc) if cfg.wide else (B, Q, Cc)
+
+
 def xview_forward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
                   offsets=None, cam_logits=None, lidar2img=None, want_mask: bool = False):
-    """One fused forward launch.  Returns (out (B,Q,C) fp32, mask uint8 or None)."""
+    """One fused forward launch.
+    narrow: returns (out (B,Q,C), mask|None);  wide: returns ((out (B,Q,Hh,C), wsum (B,Q,Hh)), mask|None)."""
     for v in values:
         _require_cuda(v, "value")
     ref = _f32c(ref, "reference_points")
@@ -198,11 +285,15 @@ def xview_forward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: i
     cam_logits = _f32c(cam_logits, "cam_logits")
     lidar2img = _f32c(lidar2img, "lidar2img")
     L, Cc = len(values), int(values[0].shape[-1])
-    _check_shapes(cfg, B, N, L, Cc, ref, attn_logits, offsets, cam_logits, lidar2img)
+    _check_shapes(cfg, B, N, L, ref, attn_logits, offsets, cam_logits, lidar2img)
     p = _fill_params(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, lidar2img)
     Q = int(ref.shape[1])
-    out = torch.empty((B, Q, Cc), device=ref.device, dtype=torch.float32)
+    out = torch.empty(_out_shape(cfg, B, Q, Cc), device=ref.device, dtype=torch.float32)
     p.out = out.data_ptr()
+    wsum = None
+    if cfg.wide:
+        wsum = torch.empty((B, Q, cfg.num_heads), device=ref.device, dtype=torch.float32)
+        p.wsum = wsum.data_ptr()
     mask = None
     if want_mask:
         shape = (B, Q, N) if cfg.mode != MODE_C else (B, N, Q, cfg.num_heads, cfg.num_points)
@@ -210,17 +301,21 @@ def xview_forward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: i
         p.mask = mask.data_ptr()
     st = _lib.load().gd4d_xview_forward(C.byref(p), _stream_ptr(ref.device))
     _lib.check(st, "gd4d_xview_forward")
-    return out, mask
+    _count()
+    return ((out, wsum) if cfg.wide else out), mask
 
 
 def xview_backward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
                    offsets, cam_logits, lidar2img, grad_out, grad_values: Optional[Sequence[torch.Tensor]],
-                   need_ref: bool = True, need_offsets: bool = True):
+                   need_ref: bool = True, need_offsets: bool = True, grad_wsum=None):
     """One fused backward launch.  ``grad_values`` (fp32 channel-last, same shapes as
     ``values``) are ACCUMULATED into; the small gradients are returned fresh."""
     grad_out = _f32c(grad_out, "grad_out")
     p = _fill_params(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, lidar2img)
     p.grad_out = grad_out.data_ptr()
+    if grad_wsum is not None:
+        grad_wsum = _f32c(grad_wsum, "grad_wsum")
+        p.grad_wsum = grad_wsum.data_ptr()
     if grad_values is not None:
         for l, gvl in enumerate(grad_values):
             if gvl.dtype != torch.float32 or gvl.shape != values[l].shape or not gvl.is_contiguous():
@@ -245,52 +340,134 @@ def xview_backward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: 
     p.grad_ref = g_ref.data_ptr() if g_ref is not None else None
     st = _lib.load().gd4d_xview_backward(C.byref(p), _stream_ptr(ref.device))
     _lib.check(st, "gd4d_xview_backward")
+    _count()
     return g_attn, g_off, g_cam, g_ref
+
+
+class PreparedLaunch:
+    """A fully-filled parameter block that can be re-launched without any host-side
+    tensor bookkeeping (kernel-only timing loops, CUDA-graph capture)."""
+
+    def __init__(self, fn, what, params, device, keepalive):
+        self._fn, self._what, self.params, self._device, self._keep = fn, what, params, device, keepalive
+
+    def launch(self):
+        st = self._fn(C.byref(self.params), _stream_ptr(self._device))
+        if st != 0:
+            _lib.check(st, self._what)
+        _count()
+
+
+def prepare_forward(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, lidar2img) -> PreparedLaunch:
+    ref, attn_logits, lidar2img = _f32c(ref, "ref"), _f32c(attn_logits, "attn"), _f32c(lidar2img, "l2i")
+    offsets, cam_logits = _f32c(offsets, "offsets"), _f32c(cam_logits, "cam")
+    _check_shapes(cfg, B, N, len(values), ref, attn_logits, offsets, cam_logits, lidar2img)
+    p = _fill_params(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, lidar2img)
+    Q, Cc = int(ref.shape[1]), int(values[0].shape[-1])
+    out = torch.empty(_out_shape(cfg, B, Q, Cc), device=ref.device, dtype=torch.float32)
+    p.out = out.data_ptr()
+    wsum = None
+    if cfg.wide:
+        wsum = torch.empty((B, Q, cfg.num_heads), device=ref.device, dtype=torch.float32)
+        p.wsum = wsum.data_ptr()
+    pl = PreparedLaunch(_lib.load().gd4d_xview_forward, "gd4d_xview_forward", p, ref.device,
+                        (list(values), ref, attn_logits, offsets, cam_logits, lidar2img, out, wsum))
+    pl.out, pl.wsum = out, wsum
+    return pl
+
+
+def prepare_backward(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, lidar2img, grad_out,
+                     grad_values, grad_wsum=None) -> PreparedLaunch:
+    """Backward launch that keeps accumulating into ``grad_values`` and one small-gradient
+    buffer (never re-zeroed: for timing only)."""
+    ref, attn_logits, lidar2img = _f32c(ref, "ref"), _f32c(attn_logits, "attn"), _f32c(lidar2img, "l2i")
+    offsets, cam_logits, grad_out = _f32c(offsets, "offsets"), _f32c(cam_logits, "cam"), _f32c(grad_out, "gout")
+    p = _fill_params(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, lidar2img)
+    p.grad_out = grad_out.data_ptr()
+    grad_wsum = _f32c(grad_wsum, "grad_wsum")
+    if grad_wsum is not None:
+        p.grad_wsum = grad_wsum.data_ptr()
+    for l, gvl in enumerate(grad_values):
+        p.grad_value[l] = gvl.data_ptr()
+    smalls = [torch.zeros_like(t) for t in (attn_logits, ref)]
+    p.grad_attn_logits, p.grad_ref = smalls[0].data_ptr(), smalls[1].data_ptr()
+    if offsets is not None:
+        smalls.append(torch.zeros_like(offsets))
+        p.grad_offsets = smalls[-1].data_ptr()
+    if cam_logits is not None:
+        smalls.append(torch.zeros_like(cam_logits))
+        p.grad_cam_logits = smalls[-1].data_ptr()
+    return PreparedLaunch(_lib.load().gd4d_xview_backward, "gd4d_xview_backward", p, ref.device,
+                          (list(values), ref, attn_logits, offsets, cam_logits, lidar2img, grad_out,
+                           grad_wsum, list(grad_values), smalls))
 
 
 # --------------------------------------------------------------------------------------
 # autograd
 # --------------------------------------------------------------------------------------
+_I_REF, _I_ATTN, _I_OFF, _I_CAM, _I_TOKEN, _I_VALUES = 3, 4, 5, 6, 8, 10
+
+
 class _XViewFn(torch.autograd.Function):
+    """inputs: cfg, B, N, ref, attn_logits, offsets, cam_logits, lidar2img, token, sink, *values
+
+    With a ``token``/``sink`` pair (shared, detached feature maps) the feature
+    gradient is accumulated into the sink and only a dummy gradient flows to the
+    token; otherwise ``values`` are differentiable inputs and get fresh fp32 grads.
+    """
+
     @staticmethod
     def forward(ctx, cfg: XViewConfig, B: int, N: int, ref, attn_logits, offsets, cam_logits, lidar2img,
-                *values):
+                token, sink, *values):
         ref_c = _f32c(ref, "reference_points")
         attn_c = _f32c(attn_logits, "attn_logits")
         off_c = _f32c(offsets, "offsets")
         cam_c = _f32c(cam_logits, "cam_logits")
         l2i_c = _f32c(lidar2img, "lidar2img")
-        out, _ = xview_forward(cfg, values, B, N, ref_c, attn_c, off_c, cam_c, l2i_c)
-        ctx.cfg, ctx.B, ctx.N = cfg, B, N
+        res, _ = xview_forward(cfg, values, B, N, ref_c, attn_c, off_c, cam_c, l2i_c)
+        ctx.cfg, ctx.B, ctx.N, ctx.sink = cfg, B, N, sink
         ctx.has_off, ctx.has_cam = offsets is not None, cam_logits is not None
-        ctx.save_for_backward(ref_c, attn_c, off_c if off_c is not None else ref_c.new_empty(0),
-                              cam_c if cam_c is not None else ref_c.new_empty(0), l2i_c, *values)
-        return out
+        empty = ref_c.new_empty(0)
+        ctx.save_for_backward(ref_c, attn_c, off_c if off_c is not None else empty,
+                              cam_c if cam_c is not None else empty, l2i_c, *values)
+        return res
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, grad_wsum=None):
         ref, attn, off, cam, l2i, *values = ctx.saved_tensors
         off = off if ctx.has_off else None
         cam = cam if ctx.has_cam else None
         nd = ctx.needs_input_grad
-        need_values = any(nd[8:])
-        grad_values = [torch.zeros(v.shape, device=v.device, dtype=torch.float32) for v in values] \
-            if need_values else None
+        use_sink = ctx.sink is not None and nd[_I_TOKEN]
+        need_values = any(nd[_I_VALUES:])
+        grad_values = None
+        if use_sink:
+            grad_values = ctx.sink.get()
+        elif need_values:
+            grad_values = [torch.zeros(v.shape, device=v.device, dtype=torch.float32) for v in values]
         g_attn, g_off, g_cam, g_ref = xview_backward(
             ctx.cfg, values, ctx.B, ctx.N, ref, attn, off, cam, l2i, grad_out, grad_values,
-            need_ref=nd[3], need_offsets=ctx.has_off and nd[5])
+            need_ref=nd[_I_REF], need_offsets=ctx.has_off and nd[_I_OFF],
+            grad_wsum=grad_wsum if ctx.cfg.wide else None)
         gv = [None] * len(values)
-        if need_values:
+        if need_values and not use_sink:
             gv = [g if g.dtype == v.dtype else g.to(v.dtype) for g, v in zip(grad_values, values)]
-        return (None, None, None, g_ref if nd[3] else None, g_attn if nd[4] else None,
-                g_off if (ctx.has_off and nd[5]) else None, g_cam if (ctx.has_cam and nd[6]) else None,
-                None, *gv)
+        g_token = grad_out.new_zeros(()) if use_sink else None
+        return (None, None, None, g_ref if nd[_I_REF] else None, g_attn if nd[_I_ATTN] else None,
+                g_off if (ctx.has_off and nd[_I_OFF]) else None,
+                g_cam if (ctx.has_cam and nd[_I_CAM]) else None, None, g_token, None, *gv)
 
 
 def xview_attention(cfg: XViewConfig, packed: PackedFeatures, ref, attn_logits, offsets=None,
                     cam_logits=None, lidar2img=None, values: Optional[Sequence[torch.Tensor]] = None):
-    """Differentiable fused cross-view sampling attention -> (B,Q,C) fp32.
+    """Differentiable fused cross-view sampling attention.
 
-    ``values`` overrides ``packed.levels`` (variant C passes the value_proj'ed maps)."""
-    vals = list(values) if values is not None else packed.levels
-    return _XViewFn.apply(cfg, packed.B, packed.N, ref, attn_logits, offsets, cam_logits, lidar2img, *vals)
+    narrow -> (B,Q,C) fp32;  wide -> (out (B,Q,Hh,C), wsum (B,Q,Hh)).
+    ``values`` (differentiable channel-last tensors, e.g. the value_proj'ed maps of the
+    dense path) override ``packed.levels``; without them the shared packed maps are
+    sampled and their gradient goes to ``packed.sink``."""
+    if values is not None:
+        return _XViewFn.apply(cfg, packed.B, packed.N, ref, attn_logits, offsets, cam_logits, lidar2img,
+                              None, None, *values)
+    return _XViewFn.apply(cfg, packed.B, packed.N, ref, attn_logits, offsets, cam_logits, lidar2img,
+                          packed.token, packed.sink, *packed.levels)

@@ -40,14 +40,14 @@ extern "C" {
 #define GD4D_API
 #endif
 
-#define GD4D_ABI_VERSION 1
+#define GD4D_ABI_VERSION 2
 #define GD4D_MAX_LEVELS 8
 
 typedef enum gd4d_status {
   GD4D_OK = 0,
   GD4D_ERR_NULL = -1,        /* required pointer is NULL                       */
   GD4D_ERR_DIMS = -2,        /* non-positive / inconsistent dimension          */
-  GD4D_ERR_HEAD_DIM = -3,    /* C/Hh is not 32 (the only head width built)     */
+  GD4D_ERR_HEAD_DIM = -3,    /* narrow: C/Hh != 32; wide: C*elem not 512/1024 B  */
   GD4D_ERR_ALIGN = -4,       /* a feature/out pointer is not 16-byte aligned   */
   GD4D_ERR_UNSUPPORTED = -5, /* unknown mode / dtype / L*P > 64 / N*P too big  */
   GD4D_ERR_CUDA = -6         /* launch failed (cudaGetLastError != success)    */
@@ -83,6 +83,19 @@ typedef enum gd4d_dtype { GD4D_F32 = 0, GD4D_BF16 = 1 } gd4d_dtype;
  * Outputs:  out (B,Q,C) fp32.
  *           mask (optional, may be NULL) uint8: A/V2 (B,Q,N); C (B,N,Q,Hh,P).
  *
+ * "Wide" sampling (mode C, wide = 1) -- gather-then-project.  The reference runs
+ * value_proj (a 256x256 Linear) over EVERY pixel of every camera in every layer
+ * (deform3d_cross_attn.py:278) and then samples head h's 32-channel slice.  By
+ * linearity  sum_s w_s * (W f_s + b) = W (sum_s w_s f_s) + b * sum_s w_s, so with
+ * wide = 1 each head samples all C channels of the RAW feature maps:
+ *   out  (B,Q,Hh,C) = sum_s w_s * bilinear(f_s)          (fp32)
+ *   wsum (B,Q,Hh)   = sum_s w_s * (in-bounds corner weight sum)   [multiplies the bias]
+ * and the caller applies W_v's head slice to `out` with one tiny batched GEMM.
+ * No dense per-layer GEMM, no per-layer copy of the maps, and in backward the
+ * feature gradient lands directly in ONE grad map shared by all decoder layers.
+ * grad_out is then (B,Q,Hh,C) and grad_wsum (B,Q,Hh).  C must be 32 lanes * 16 B
+ * * {1,2}: fp32 C in {128,256}, bf16 C in {256,512}.
+ *
  * Backward (gd4d_xview_backward) reads grad_out (B,Q,C) and ACCUMULATES with
  * atomics into caller-zeroed buffers; any grad pointer may be NULL to skip it:
  *   grad_value[l] fp32 channel-last, same shape as value[l]
@@ -93,6 +106,7 @@ typedef struct gd4d_xview_params {
   int32_t mode;                 /* gd4d_mode  */
   int32_t value_dtype;          /* gd4d_dtype */
   int32_t B, Q, N, Hh, L, P, C;
+  int32_t wide;                 /* mode C only: 0 = head slices of projected value, 1 = see above */
   int32_t level_h[GD4D_MAX_LEVELS];
   int32_t level_w[GD4D_MAX_LEVELS];
   float pc_lo[3];               /* pc_range[0:3]                              */
@@ -107,9 +121,11 @@ typedef struct gd4d_xview_params {
   const float* offsets;
   const float* cam_logits;
   float* out;
+  float* wsum;                  /* wide only */
   uint8_t* mask;
   /* backward only */
   const float* grad_out;
+  const float* grad_wsum;       /* wide only, may be NULL (treated as zeros) */
   float* grad_value[GD4D_MAX_LEVELS];
   float* grad_value_bias;
   float* grad_attn_logits;
@@ -119,6 +135,8 @@ typedef struct gd4d_xview_params {
 } gd4d_xview_params;
 
 GD4D_API int gd4d_abi_version(void);
+/* sizeof(gd4d_xview_params) as compiled, so FFI mirrors can check their layout */
+GD4D_API int gd4d_params_size(void);
 GD4D_API const char* gd4d_strerror(int status);
 
 /* bytes of dynamic shared memory / CTAs the forward launch will use (for tests

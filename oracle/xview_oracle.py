@@ -62,10 +62,24 @@ def project(points: torch.Tensor, lidar2img: torch.Tensor, img_h, img_w):
     size, depth mask (B,N,M,1).  detr3d_transformer.py:409-420."""
     B, M = points.shape[:2]
     N = lidar2img.size(1)
-    pts = torch.cat((points, torch.ones_like(points[..., :1])), -1)
-    pts = pts.view(B, 1, M, 4).repeat(1, N, 1, 1).unsqueeze(-1)
-    mats = lidar2img.view(B, N, 1, 4, 4).repeat(1, 1, M, 1, 1)
-    cam = torch.matmul(mats, pts).squeeze(-1)
+    # The reference materialises (B,N,M,4,4)@(B,N,M,4,1) with torch.matmul (:412-414).
+    # torch's CPU kernel evaluates each row as the sequential, non-fused
+    # ((m0*x + m1*y) + m2*z) + m3*1 (SURVEY A.2); it is written out here with
+    # elementwise ops so the result cannot depend on which BLAS / CPU runs the
+    # oracle.  tests/test_oracle_vs_reference.py checks bit-equality with the
+    # reference's own matmul.
+    X = points[..., 0].view(B, 1, M)
+    Y = points[..., 1].view(B, 1, M)
+    Z = points[..., 2].view(B, 1, M)
+    m = lidar2img.view(B, N, 16, 1)
+    rows = []
+    for r in range(3):
+        acc = m[:, :, 4 * r + 0] * X
+        acc = acc + m[:, :, 4 * r + 1] * Y
+        acc = acc + m[:, :, 4 * r + 2] * Z
+        acc = acc + m[:, :, 4 * r + 3] * torch.ones_like(X)
+        rows.append(acc)
+    cam = torch.stack(rows, -1)                            # (B,N,M,3)
     mask = cam[..., 2:3] > EPS
     uv = cam[..., 0:2] / torch.maximum(cam[..., 2:3], torch.ones_like(cam[..., 2:3]) * EPS)
     uv[..., 0] /= img_w
@@ -171,6 +185,25 @@ def xview_c_core(values, reference_points, offsets, attn_logits, cam_logits, lid
     out = msda_pytorch(value, shapes, locs, aw.view(B * N, Q, Hh, L, P))    # :301-309
     out = out.view(B, N, Q, -1) * camw.sigmoid()                            # :320-323
     return out.sum(1), mask.view(B, N, Q, Hh, L, P)                         # :324
+
+
+def xview_c_wide_core(feats, reference_points, offsets, attn_logits, cam_logits, lidar2img,
+                      pc_range, img_h, img_w, num_heads):
+    """Gather-then-project restatement: every head samples ALL C raw channels with its
+    own points/weights.  Built from ``xview_c_core`` itself (features repeated once per
+    head, so head h's "slice" is the whole map) -- no new arithmetic.
+    Returns agg (B,Q,Hh,C) and wsum (B,Q,Hh) = the same sampling of an all-ones map
+    (zeros outside the image), which is what multiplies value_proj's bias:
+        sum_s w_s (W f_s + b) = W agg + b wsum      (deform3d_cross_attn.py:278-324)."""
+    B, Q = reference_points.shape[:2]
+    C = feats[0].shape[2]
+    rep = [f.repeat(1, 1, num_heads, 1, 1) for f in feats]
+    agg, _ = xview_c_core(rep, reference_points, offsets, attn_logits, cam_logits, lidar2img,
+                          pc_range, img_h, img_w, num_heads)
+    ones = [torch.ones_like(f[:, :, :1]).repeat(1, 1, num_heads, 1, 1) for f in feats]
+    wsum, _ = xview_c_core(ones, reference_points, offsets, attn_logits, cam_logits, lidar2img,
+                           pc_range, img_h, img_w, num_heads)
+    return agg.view(B, Q, num_heads, C), wsum.view(B, Q, num_heads)
 
 
 # --------------------------------------------------------------------------

@@ -1,0 +1,73 @@
+"""The C-ABI library loads without a GPU and exports every symbol the header
+declares; parameter validation (which runs before any launch) returns the
+documented status codes."""
+import ctypes as C
+import os
+import re
+
+from graph_detr4d_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "gd4d_xview.h")).read()
+    return re.findall(r"GD4D_API\s+[\w\s\*]+?\b(gd4d_\w+)\s*\(", src)
+
+
+def test_every_declared_symbol_is_exported():
+    lib = _lib.load()
+    names = _declared()
+    assert set(names) == set(_lib.EXPORTS) and len(names) >= 7
+    for n in names:
+        assert getattr(lib, n) is not None
+
+
+def test_struct_layout_and_version():
+    lib = _lib.load()
+    assert lib.gd4d_abi_version() == _lib.ABI_VERSION
+    assert lib.gd4d_params_size() == C.sizeof(_lib.XViewParams)
+
+
+def _valid_params():
+    p = _lib.XViewParams()
+    p.abi_version = _lib.ABI_VERSION
+    p.mode, p.value_dtype = _lib.MODE_C, _lib.F32
+    p.B, p.Q, p.N, p.Hh, p.L, p.P, p.C = 1, 900, 12, 8, 4, 4, 256
+    for l, (h, w) in enumerate([(116, 200), (58, 100), (29, 50), (15, 25)]):
+        p.level_h[l], p.level_w[l] = h, w
+        p.value[l] = 0x1000 * (l + 1)            # fake, aligned, never dereferenced on the host
+    p.img_h, p.img_w = 900.0, 1600.0
+    p.ref = p.lidar2img = p.attn_logits = p.offsets = p.cam_logits = p.out = 0x10000
+    return p
+
+
+def test_launch_info_and_status_codes():
+    lib = _lib.load()
+    p = _valid_params()
+    g, b, s = C.c_int32(), C.c_int32(), C.c_int32()
+    assert lib.gd4d_xview_launch_info(C.byref(p), C.byref(g), C.byref(b), C.byref(s)) == 0
+    assert b.value == 256 and g.value == 900 and s.value > 0
+    assert lib.gd4d_xview_launch_info(None, None, None, None) == -1
+    q = _valid_params(); q.abi_version = 7
+    assert lib.gd4d_xview_launch_info(C.byref(q), None, None, None) == -5
+    q = _valid_params(); q.Q = 0
+    assert lib.gd4d_xview_launch_info(C.byref(q), None, None, None) == -2
+    q = _valid_params(); q.C = 512
+    assert lib.gd4d_xview_launch_info(C.byref(q), None, None, None) == -3
+    q = _valid_params(); q.value[2] = 0x1004
+    assert lib.gd4d_xview_launch_info(C.byref(q), None, None, None) == -4
+    q = _valid_params(); q.value[1] = None
+    assert lib.gd4d_xview_launch_info(C.byref(q), None, None, None) == -1
+    q = _valid_params(); q.offsets = None
+    assert lib.gd4d_xview_launch_info(C.byref(q), None, None, None) == -1
+    q = _valid_params(); q.P = 32                                   # L*P = 128 > 64
+    assert lib.gd4d_xview_launch_info(C.byref(q), None, None, None) == -5
+    q = _valid_params(); q.mode = 7
+    assert lib.gd4d_xview_launch_info(C.byref(q), None, None, None) == -5
+    q = _valid_params(); q.grad_out = None
+    assert lib.gd4d_xview_backward(C.byref(q), None) == -1          # validation precedes any launch
+    assert lib.gd4d_pack_nchw(None, None, 0, 0, 1, 1, 1, 1, None) == -1
+    assert lib.gd4d_pack_nchw(0x1000, 0x2000, 0, 0, 0, 1, 1, 1, None) == -2
+    for code in (0, -1, -2, -3, -4, -5, -6, -99):
+        assert len(_lib.strerror(code)) > 0

@@ -1,0 +1,60 @@
+"""The oracle restatement vs the committed golden vectors (reference outputs frozen
+by tests/golden/make_golden.py).  Runs anywhere -- no reference tree needed."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from graph_detr4d_b200 import synthetic as syn
+from oracle import xview_oracle as xo
+from tests import helpers as H
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+warnings.filterwarnings("ignore", message="Default grid_sample")
+
+
+def load_golden(variant):
+    z = np.load(os.path.join(GOLD, f"module_{variant}.npz"))
+    T = int(z["num_frames"])
+    feats = []
+    i = 0
+    while f"feat{i}_bf16" in z:
+        bits = torch.from_numpy(z[f"feat{i}_bf16"].copy())
+        feats.append(bits.view(torch.bfloat16).float())
+        i += 1
+    sd = {k[3:]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith("sd.")}
+    l2i = z["lidar2img"]
+    metas = [dict(lidar2img=[l2i[n] for n in range(l2i.shape[0])], img_shape=[syn.IMG_SHAPE] * l2i.shape[0])]
+    t = lambda k: torch.from_numpy(z[k].copy())
+    return dict(z=z, T=T, feats=feats, sd=sd, metas=metas, query=t("query"), query_pos=t("query_pos"),
+                ref=t("ref"), gout=t("gout"), out=t("out"), grad_query=t("grad_query"), grad_ref=t("grad_ref"),
+                grad_feats=[t(f"grad_feat{j}") for j in range(i)])
+
+
+@pytest.mark.parametrize("variant", ["A", "C"])
+def test_oracle_reproduces_golden(variant):
+    gd = load_golden(variant)
+    feats = [f.clone().requires_grad_(True) for f in gd["feats"]]
+    q = gd["query"].clone().requires_grad_(True)
+    rp = gd["ref"].clone().requires_grad_(True)
+    if variant == "A":
+        y = xo.detr3d_cross_atten_forward(gd["sd"], q, feats, gd["query_pos"], rp, gd["metas"], syn.PC_RANGE)
+    else:
+        y = xo.deform3d_cross_attn_forward(gd["sd"], q, feats, gd["query_pos"], rp, gd["metas"],
+                                           syn.PC_RANGE, num_heads=2)
+    (y * gd["gout"]).sum().backward()
+    assert H.rel_err(y.detach(), gd["out"]) <= 2e-6
+    assert H.rel_err(q.grad, gd["grad_query"]) <= 1e-5
+    assert H.rel_err(rp.grad, gd["grad_ref"]) <= 1e-5
+    for f, gref in zip(feats, gd["grad_feats"]):
+        assert H.rel_err(f.grad, gref) <= 1e-5
+
+
+def test_golden_mask_bit_exact():
+    gd = load_golden("A")
+    l2i = xo.lidar2img_tensor(gd["metas"], gd["ref"])
+    _, mask = xo.feature_sampling_a(gd["feats"], gd["ref"], syn.PC_RANGE, l2i, 900, 1600)
+    gold = torch.from_numpy(gd["z"]["mask"].copy())
+    assert gold.dtype == torch.bool and torch.equal(mask, gold) and gold.any()

@@ -177,3 +177,64 @@ def test_error_codes():
     p.B = p.Q = p.N = p.L = p.P = 1
     p.Hh, p.C = 8, 128                                           # head width 16
     assert lib.gd4d_xview_forward(C.byref(p), None) == -3
+
+
+# ------------------------------------------------------------------------------------------
+# wide (gather-then-project) mode
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,dtype,T,Q", [(256, torch.float32, 2, 96), (128, torch.float32, 1, 50),
+                                         (256, torch.bfloat16, 2, 64), (512, torch.bfloat16, 1, 20)])
+def test_mode_c_wide_forward_backward(C, dtype, T, Q):
+    sc = H.scene(B=1, T=T, Q=Q, C=C)
+    logits, offsets, cam = H.rand_inputs_c(sc, P=4)
+    g = torch.Generator().manual_seed(10)
+    g1 = torch.randn(1, Q, 8, C, generator=g)
+    g2 = torch.randn(1, Q, 8, generator=g)
+    feats_src = [f.to(dtype).float() for f in sc["feats"]]
+    feats_o = [_leaf(f) for f in feats_src]
+    ref_o, log_o, off_o, cam_o = _leaf(sc["ref"]), _leaf(logits), _leaf(offsets), _leaf(cam)
+    agg_o, ws_o = xo.xview_c_wide_core(feats_o, ref_o, off_o, log_o, cam_o, sc["l2i"], syn.PC_RANGE,
+                                       900, 1600, 8)
+    ((agg_o * g1).sum() + (ws_o * g2).sum()).backward()
+
+    feats_g = [_leaf(f.cuda()) for f in feats_src]
+    ref_g, log_g, off_g, cam_g = (_leaf(t.cuda()) for t in (sc["ref"], logits, offsets, cam))
+    packed = ops.pack_features(feats_g, dtype)
+    assert packed.token is not None and packed.levels[0].dtype == dtype
+    cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=True)
+    agg, ws = ops.xview_attention(cfg, packed, ref_g, log_g, off_g, cam_g, sc["l2i"].cuda())
+    assert tuple(agg.shape) == (1, Q, 8, C) and tuple(ws.shape) == (1, Q, 8)
+    ((agg * g1.cuda()).sum() + (ws * g2.cuda()).sum()).backward()
+    assert H.rel_err(agg.detach().cpu(), agg_o.detach()) <= FWD_TOL
+    assert H.rel_err(ws.detach().cpu(), ws_o.detach()) <= FWD_TOL
+    assert H.rel_err(log_g.grad.cpu(), log_o.grad) <= GRAD_TOL
+    assert H.rel_err(cam_g.grad.cpu(), cam_o.grad) <= GRAD_TOL
+    assert H.rel_err(off_g.grad.cpu(), off_o.grad) <= GRAD_TOL
+    assert H.rel_err(ref_g.grad.cpu(), ref_o.grad) <= GRAD_TOL
+    for fg, fo in zip(feats_g, feats_o):
+        assert fg.grad.dtype == torch.float32
+        assert H.rel_err(fg.grad.cpu(), fo.grad) <= GRAD_TOL
+
+
+def test_grad_sink_is_shared_across_layers():
+    """Six 'layers' sampling the same packed maps must accumulate into ONE grad map."""
+    sc = H.scene(B=1, T=1, Q=40)
+    feats_g = [_leaf(f.cuda()) for f in sc["feats"]]
+    packed = ops.pack_features(feats_g)
+    cfg = XViewConfig(MODE_A, 8, 1, tuple(syn.PC_RANGE), 900.0, 1600.0)
+    total = 0
+    for i in range(3):
+        logits = H.rand_inputs_a(sc, seed=20 + i).cuda()
+        total = total + ops.xview_attention(cfg, packed, sc["ref"].cuda(), logits,
+                                            lidar2img=sc["l2i"].cuda()).sum()
+    total.backward()
+    assert packed.sink.buffers is None                       # handed over exactly once
+    feats_o = [_leaf(f) for f in sc["feats"]]
+    tot_o = 0
+    for i in range(3):
+        out_o, _ = xo.xview_a_core(feats_o, sc["ref"], H.rand_inputs_a(sc, seed=20 + i), sc["l2i"],
+                                   syn.PC_RANGE, 900, 1600)
+        tot_o = tot_o + out_o.sum()
+    tot_o.backward()
+    for fg, fo in zip(feats_g, feats_o):
+        assert H.rel_err(fg.grad.cpu(), fo.grad) <= GRAD_TOL

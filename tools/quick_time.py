@@ -20,21 +20,24 @@ def timeit(fn, iters=50, warm=5, flush=None):
 
 res = {}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-for name, mode, T, dtype in [("C_T2_fp32", MODE_C, 2, torch.float32), ("C_T2_bf16", MODE_C, 2, torch.bfloat16),
-                             ("A_T1_fp32", MODE_A, 1, torch.float32), ("C_T1_fp32", MODE_C, 1, torch.float32)]:
+import sys as _s
+WIDE = "--narrow" not in _s.argv
+for name, mode, T, dtype in [("C_T1_fp32", MODE_C, 1, torch.float32), ("C_T2_fp32", MODE_C, 2, torch.float32),
+                             ("C_T2_bf16", MODE_C, 2, torch.bfloat16), ("A_T1_fp32", MODE_A, 1, torch.float32)]:
     sc = H.scene(B=1, T=T, Q=900, shapes=H.FULL_SHAPES)
     t0 = time.time()
     packed = ops.pack_features([f.cuda() for f in sc["feats"]], dtype)
     ref = sc["ref"].cuda(); l2i = sc["l2i"].cuda()
     if mode == MODE_C:
         logits, offsets, cam = (t.cuda() for t in H.rand_inputs_c(sc))
-        cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0)
+        cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=WIDE)
         fwd = lambda: ops.xview_forward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i)
     else:
         logits = H.rand_inputs_a(sc).cuda(); offsets = cam = None
         cfg = XViewConfig(MODE_A, 8, 1, tuple(syn.PC_RANGE), 900.0, 1600.0)
         fwd = lambda: ops.xview_forward(cfg, packed.levels, 1, sc["N"], ref, logits, lidar2img=l2i)
     out, mask = ops.xview_forward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i, want_mask=True)
+    if isinstance(out, tuple): out = out[0]
     gout = torch.randn_like(out)
     gvals = [torch.zeros(v.shape, device='cuda', dtype=torch.float32) for v in packed.levels]
     bwd = lambda: ops.xview_backward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i, gout, gvals)
