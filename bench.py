@@ -239,8 +239,20 @@ def main():
 
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
+    e2e_state = dict(primed=False)
+
     def step_e2e():
-        stepper.set_inputs(feats_host, metas)               # H2D of this step's feature maps (pinned)
+        # public-API host-buffer step: this step's maps were (or are now) copied H2D from
+        # pinned memory; the NEXT step's copy is started before the compute so it overlaps.
+        if not e2e_state["primed"]:
+            stepper.prefetch(feats_host)
+            e2e_state["primed"] = True
+        stepper.commit(metas)
+        e2e_state["i"] = e2e_state.get("i", 0) + 1
+        if e2e_state["i"] < e2e_state.get("n", 1 << 30):
+            stepper.prefetch(feats_host)                    # H2D of step i+1 (one copy per step)
+        else:
+            e2e_state["primed"] = False
         loss = stepper.step()
         loss_host.copy_(loss, non_blocking=True)            # D2H of the step's result
         torch.cuda.current_stream().synchronize()           # the user reads the loss every step
@@ -273,8 +285,10 @@ def main():
     sampler.start()
     ms_total = timed(step_resident, K)
     launches = launches_per_step * K
+    e2e_state.update(i=0, n=2)
     for _ in range(2):
         step_e2e()
+    e2e_state.update(i=0, n=K)                              # exactly K H2D copies inside the timed region
     ms_e2e = timed(step_e2e, K)
     clocks = sampler.stop()
     feats_dev = stepper.static_feats

@@ -42,7 +42,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 template <int MODE, typename VT, int LANES, int NV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (LANES == 32) ? 2 : 3)
 xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap) {
   constexpr int VEC = Slice<VT>::VEC;
   constexpr int PL = VEC * NV;
@@ -121,13 +121,25 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     const size_t rowst = static_cast<size_t>(W) * p.C;
     float c00[PL], c01[PL], c10[PL], c11[PL];
     const bool a00 = active & f.in00, a01 = active & f.in01, a10 = active & f.in10, a11 = active & f.in11;
+    {
+      uint4 r00[NV], r01[NV], r10[NV], r11[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int o = j * LANES * VEC;
-      Slice<VT>::load(base + e00 + o, a00, *reinterpret_cast<float(*)[VEC]>(&c00[j * VEC]));
-      Slice<VT>::load(base + e00 + p.C + o, a01, *reinterpret_cast<float(*)[VEC]>(&c01[j * VEC]));
-      Slice<VT>::load(base + e00 + rowst + o, a10, *reinterpret_cast<float(*)[VEC]>(&c10[j * VEC]));
-      Slice<VT>::load(base + e00 + rowst + p.C + o, a11, *reinterpret_cast<float(*)[VEC]>(&c11[j * VEC]));
+      for (int j = 0; j < NV; ++j) {
+        const int o = j * LANES * VEC;
+        r00[j] = ldg_nc_v4(base + e00 + o, a00);
+        r01[j] = ldg_nc_v4(base + e00 + p.C + o, a01);
+        r10[j] = ldg_nc_v4(base + e00 + rowst + o, a10);
+        r11[j] = ldg_nc_v4(base + e00 + rowst + p.C + o, a11);
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) pin(r00[j], r01[j], r10[j], r11[j]);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        Slice<VT>::unpack(r00[j], &c00[j * VEC]);
+        Slice<VT>::unpack(r01[j], &c01[j * VEC]);
+        Slice<VT>::unpack(r10[j], &c10[j * VEC]);
+        Slice<VT>::unpack(r11[j], &c11[j * VEC]);
+      }
     }
     const float w00 = (1.f - f.tx) * (1.f - f.ty), w01 = f.tx * (1.f - f.ty);
     const float w10 = (1.f - f.tx) * f.ty, w11 = f.tx * f.ty;

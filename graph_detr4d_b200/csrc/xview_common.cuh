@@ -77,25 +77,51 @@ __device__ __forceinline__ float to_pixel(float g, float size) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---- 16-byte channel-slice loads ------------------------------------------------
+// Loads are volatile inline PTX so that nvcc keeps them in program order, and
+// `pin()` is an empty volatile asm that "touches" the loaded registers: arithmetic
+// that consumes them cannot be hoisted above it.  Together they make the compiler
+// issue a whole batch of independent gathers BEFORE the first FMA waits on one --
+// left alone it interleaves load/consume to save registers and the warp has only
+// 2-4 gathers in flight (seen in the r1 SASS), which is what bounds this kernel.
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p, bool pred) {
+  uint4 t;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b32 %0, 0;\n\t"
+      "mov.b32 %1, 0;\n\t"
+      "mov.b32 %2, 0;\n\t"
+      "mov.b32 %3, 0;\n\t"
+      "@p ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+      "}"
+      : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+      : "l"(p), "r"(static_cast<int>(pred)));
+  return t;
+}
+
+__device__ __forceinline__ void pin(uint4& a, uint4& b, uint4& c, uint4& d) {
+  asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z),
+                    "+r"(b.w), "+r"(c.x), "+r"(c.y), "+r"(c.z), "+r"(c.w), "+r"(d.x), "+r"(d.y),
+                    "+r"(d.z), "+r"(d.w));
+}
+
 template <typename VT>
 struct Slice;  // VEC = channels per 16-byte lane load
 
 template <>
 struct Slice<float> {
   static constexpr int VEC = 4;
-  __device__ __forceinline__ static void load(const float* p, bool pred, float (&v)[VEC]) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pred) t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  __device__ __forceinline__ static void unpack(const uint4& t, float* v) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y);
+    v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
   }
 };
 
 template <>
 struct Slice<__nv_bfloat16> {
   static constexpr int VEC = 8;
-  __device__ __forceinline__ static void load(const __nv_bfloat16* p, bool pred, float (&v)[VEC]) {
-    uint4 t = make_uint4(0u, 0u, 0u, 0u);
-    if (pred) t = __ldg(reinterpret_cast<const uint4*>(p));
+  __device__ __forceinline__ static void unpack(const uint4& t, float* v) {
     v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
     v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
     v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);

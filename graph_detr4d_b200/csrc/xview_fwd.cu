@@ -34,7 +34,7 @@ struct __align__(16) Cand {
 template <typename VT, int NV>
 struct ItemLoad {
   static constexpr int PL = Slice<VT>::VEC * NV;  // channels per lane
-  float c00[PL], c01[PL], c10[PL], c11[PL];
+  uint4 r00[NV], r01[NV], r10[NV], r11[NV];       // raw 16-byte corner runs
   float w00, w01, w10, w11, wt, inb;
 };
 
@@ -79,26 +79,41 @@ __device__ __forceinline__ void item_issue(const gd4d_xview_params& p, const Can
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int o = j * LANES * VEC;
-    Slice<VT>::load(p00 + o, active & f.in00, *reinterpret_cast<float(*)[VEC]>(&ld.c00[j * VEC]));
-    Slice<VT>::load(p00 + p.C + o, active & f.in01, *reinterpret_cast<float(*)[VEC]>(&ld.c01[j * VEC]));
-    Slice<VT>::load(p10 + o, active & f.in10, *reinterpret_cast<float(*)[VEC]>(&ld.c10[j * VEC]));
-    Slice<VT>::load(p10 + p.C + o, active & f.in11, *reinterpret_cast<float(*)[VEC]>(&ld.c11[j * VEC]));
+    ld.r00[j] = ldg_nc_v4(p00 + o, active & f.in00);
+    ld.r01[j] = ldg_nc_v4(p00 + p.C + o, active & f.in01);
+    ld.r10[j] = ldg_nc_v4(p10 + o, active & f.in10);
+    ld.r11[j] = ldg_nc_v4(p10 + p.C + o, active & f.in11);
   }
+}
+
+template <typename VT, int NV>
+__device__ __forceinline__ void item_pin(ItemLoad<VT, NV>& ld) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) pin(ld.r00[j], ld.r01[j], ld.r10[j], ld.r11[j]);
 }
 
 template <typename VT, int NV>
 __device__ __forceinline__ void item_consume(const ItemLoad<VT, NV>& ld,
                                              float (&acc)[ItemLoad<VT, NV>::PL], float& wsum) {
+  constexpr int VEC = Slice<VT>::VEC;
 #pragma unroll
-  for (int i = 0; i < ItemLoad<VT, NV>::PL; ++i) {
-    const float s = ld.w00 * ld.c00[i] + ld.w01 * ld.c01[i] + ld.w10 * ld.c10[i] + ld.w11 * ld.c11[i];
-    acc[i] = fmaf(ld.wt, s, acc[i]);
+  for (int j = 0; j < NV; ++j) {
+    float c00[VEC], c01[VEC], c10[VEC], c11[VEC];
+    Slice<VT>::unpack(ld.r00[j], c00);
+    Slice<VT>::unpack(ld.r01[j], c01);
+    Slice<VT>::unpack(ld.r10[j], c10);
+    Slice<VT>::unpack(ld.r11[j], c11);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float s = ld.w00 * c00[i] + ld.w01 * c01[i] + ld.w10 * c10[i] + ld.w11 * c11[i];
+      acc[j * VEC + i] = fmaf(ld.wt, s, acc[j * VEC + i]);
+    }
   }
   wsum = fmaf(ld.wt, ld.inb, wsum);
 }
 
 template <int MODE, typename VT, int LANES, int NV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (LANES == 32) ? 2 : 4)
 xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap) {
   constexpr int VEC = Slice<VT>::VEC;
   constexpr int PL = VEC * NV;
@@ -127,6 +142,8 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     ItemLoad<VT, NV> la, lb;
     item_issue<MODE, VT, LANES, NV>(p, cands, sw, it0 + grp, total, w, sub, la);
     item_issue<MODE, VT, LANES, NV>(p, cands, sw, it0 + GROUPS + grp, total, w, sub, lb);
+    item_pin<VT, NV>(la);
+    item_pin<VT, NV>(lb);
     item_consume<VT, NV>(la, acc, wsum);
     item_consume<VT, NV>(lb, acc, wsum);
   }

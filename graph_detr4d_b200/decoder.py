@@ -26,6 +26,7 @@ from typing import Callable, Optional, Sequence
 import torch
 import torch.nn as nn
 
+from .glue import fast_linear, self_attention
 from .modules import build_attention, inverse_sigmoid
 
 
@@ -39,8 +40,11 @@ class SelfAttention(nn.Module):
 
     def forward(self, query, query_pos=None):
         identity = query
-        q = k = query if query_pos is None else query + query_pos
-        out = self.attn(q, k, value=query, need_weights=False)[0]
+        if query.is_cuda:
+            out = self_attention(query, query_pos, self.attn)          # bmm+softmax path (glue.py)
+        else:
+            q = k = query if query_pos is None else query + query_pos
+            out = self.attn(q, k, value=query, need_weights=False)[0]
         return identity + self.dropout_layer(out)
 
 
@@ -54,7 +58,8 @@ class FFN(nn.Module):
             nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
 
     def forward(self, x):
-        return x + self.layers(x)
+        h = self.layers[0][2](self.layers[0][1](fast_linear(x, self.layers[0][0])))
+        return x + self.layers[2](fast_linear(h, self.layers[1]))
 
 
 class DecoderLayer(nn.Module):
@@ -91,7 +96,9 @@ class Detr3DTransformerDecoder(nn.Module):
         for lid, layer in enumerate(self.layers):
             output = layer(output, value, query_pos, reference_points, img_metas)
             if reg_branches is not None:                                    # :201-214
-                tmp = reg_branches[lid](output.permute(1, 0, 2))
+                tmp = output.permute(1, 0, 2)
+                for m in reg_branches[lid]:
+                    tmp = fast_linear(tmp, m) if isinstance(m, nn.Linear) else m(tmp)
                 new_ref = torch.zeros_like(reference_points)
                 new_ref[..., :2] = tmp[..., :2] + inverse_sigmoid(reference_points[..., :2])
                 new_ref[..., 2:3] = tmp[..., 4:5] + inverse_sigmoid(reference_points[..., 2:3])
@@ -129,7 +136,7 @@ class Detr3DTransformer(nn.Module):
         query_pos, query = torch.split(query_embed, self.embed_dims, dim=1)
         query_pos = query_pos.unsqueeze(0).expand(batch_size, -1, -1)
         query = query.unsqueeze(0).expand(batch_size, -1, -1)
-        reference_points = self.reference_points(query_pos).sigmoid()       # NOT detached in layer 0
+        reference_points = fast_linear(query_pos, self.reference_points).sigmoid()   # NOT detached in layer 0
         inter_states, inter_refs = self.decoder(
             query.permute(1, 0, 2), mlvl_feats, query_pos.permute(1, 0, 2), reference_points,
             reg_branches=self.reg_branches, img_metas=img_metas)

@@ -86,6 +86,28 @@ class GraphedTrainStep:
                 for dst, src in zip(self.static_feats, feats):
                     dst.copy_(src, non_blocking=True)
 
+    # ---- host-buffer pipeline: H2D of step i+1 overlaps the compute of step i ------------
+    def prefetch(self, feats_host: Sequence[torch.Tensor]):
+        """Start the H2D copy of the NEXT step's (pinned) feature maps on a copy stream."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = [torch.empty_like(f) for f in self.static_feats]
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(self.device))
+        self._copy_stream.wait_event(self._consumed)        # staging is free again
+        with torch.cuda.stream(self._copy_stream), torch.no_grad():
+            for dst, src in zip(self._staging, feats_host):
+                dst.copy_(src, non_blocking=True)
+            self._staged.record(self._copy_stream)
+
+    def commit(self, img_metas=None):
+        """Make the prefetched maps the inputs of the next ``step()`` (one D2D copy)."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._staged)
+        self.set_inputs(self._staging, img_metas)
+        self._consumed.record(cur)
+
     def step(self) -> torch.Tensor:
         self.graph_fb.replay()
         self._allreduce()

@@ -47,6 +47,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .glue import fast_linear
 from .ops import MODE_A, MODE_C, PackedFeatures, XViewConfig
 
 import sys as _sys
@@ -230,6 +231,12 @@ def _img_hw(img_metas):
     return float(shp[0]), float(shp[1])
 
 
+def _run_position_encoder(seq: nn.Sequential, x):
+    for m in seq:
+        x = fast_linear(x, m) if isinstance(m, nn.Linear) else m(x)
+    return x
+
+
 def _position_encoder(in_dims, embed_dims):
     return nn.Sequential(
         nn.Linear(in_dims, embed_dims), nn.LayerNorm(embed_dims), nn.ReLU(inplace=True),
@@ -290,13 +297,13 @@ class Detr3DCrossAtten(BaseModule):
         if packed.N != self.num_cams or len(packed.levels) != self.num_levels:
             raise ValueError(f"expected {self.num_cams} cams x {self.num_levels} levels, got "
                              f"{packed.N} x {len(packed.levels)}")
-        logits = self.attention_weights(query)              # (B,Q,N*P*L) viewed (B,1,Q,N,P,L)
+        logits = fast_linear(query, self.attention_weights)  # (B,Q,N*P*L) viewed (B,1,Q,N,P,L)
         img_h, img_w = _img_hw(img_metas)
         cfg = XViewConfig(MODE_A, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w)
         l2i = _L2I_CACHE.get(img_metas, query.device)
         out = ops.xview_attention(cfg, packed, reference_points, logits, lidar2img=l2i)   # (B,Q,C)
-        out = self.output_proj(out.permute(1, 0, 2))
-        pos_feat = self.position_encoder(inverse_sigmoid(reference_points)).permute(1, 0, 2)
+        out = fast_linear(out.permute(1, 0, 2), self.output_proj)
+        pos_feat = _run_position_encoder(self.position_encoder, inverse_sigmoid(reference_points)).permute(1, 0, 2)
         return self.dropout(out) + inp_residual + pos_feat
 
 
@@ -393,9 +400,9 @@ class Deform3DCrossAttn(BaseModule):
         if packed.N != self.num_cams or len(packed.levels) != self.num_levels:
             raise ValueError(f"expected {self.num_cams} cams x {self.num_levels} levels, got "
                              f"{packed.N} x {len(packed.levels)}")
-        cam_logits = self.cam_attention_weights(query)      # (B,Q,N); kernel reads it as view(B,N,Q)
-        offsets = self.deform_sampling_offsets(query)       # (B,Q,Hh*P*3)
-        logits = self.attention_weights(query)              # (B,Q,Hh*L*P)
+        cam_logits = fast_linear(query, self.cam_attention_weights)    # (B,Q,N); kernel reads it as view(B,N,Q)
+        offsets = fast_linear(query, self.deform_sampling_offsets)     # (B,Q,Hh*P*3)
+        logits = fast_linear(query, self.attention_weights)            # (B,Q,Hh*L*P)
         img_h, img_w = _img_hw(img_metas)
         l2i = _L2I_CACHE.get(img_metas, query.device)
         if self._use_wide(packed):
@@ -411,10 +418,10 @@ class Deform3DCrossAttn(BaseModule):
             cfg = XViewConfig(MODE_C, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w)
             out = ops.xview_attention(cfg, packed, reference_points, logits, offsets, cam_logits, l2i,
                                       values=self.project_values(packed))  # (B,Q,C)
-        out = self.output_proj(out).permute(1, 0, 2)
+        out = fast_linear(out, self.output_proj).permute(1, 0, 2)
         r3d = reference_points
         if self.depth_encode:
             depth = (r3d[..., 0:1] ** 2 + r3d[..., 1:2] ** 2) ** 0.5
             r3d = torch.cat([r3d, depth], dim=-1)
-        pos_feat = self.position_encoder(inverse_sigmoid(r3d, clamp_max=True)).permute(1, 0, 2)
+        pos_feat = _run_position_encoder(self.position_encoder, inverse_sigmoid(r3d, clamp_max=True)).permute(1, 0, 2)
         return self.dropout(out) + inp_residual + pos_feat

@@ -90,7 +90,7 @@ def test_cuda_graph_step_matches_eager():
     # Adam normalises the update to ~lr whatever the gradient's size, so parameters whose
     # gradient is near the fp32-atomics noise floor may differ by a fraction of 5*lr = 1e-3
     for pe, pg in zip(eager.parameters(), graphed.parameters()):
-        assert float((pg.detach() - pe.detach()).abs().max()) <= 1e-4
+        assert float((pg.detach() - pe.detach()).abs().max()) <= 3e-4
     # new inputs flow through the captured pack kernels (no stale packed maps)
     stepper.set_inputs([f * 0.5 for f in feats], metas)
     l_new = float(stepper.step())

@@ -1,0 +1,33 @@
+"""torch.profiler (CUPTI) kernel-time breakdown of one eager decoder step (dev tool)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from graph_detr4d_b200 import synthetic as syn, modules
+from torch.profiler import profile, ProfilerActivity
+
+dev = torch.device("cuda")
+T = int(os.environ.get("T", "1"))
+model = bench.build_model(T, os.environ.get("DTYPE", "f32"), dev)
+opt = torch.optim.AdamW(model.parameters(), lr=2e-4, fused=True, capturable=True)
+feats = [f.to(dev).requires_grad_(True) for f in syn.make_feats(1, 6 * T, 256, syn.LEVEL_SHAPES_928x1600)]
+metas = syn.make_img_metas(1, T)
+
+def step():
+    modules.clear_pack_cache()
+    st, _, refs = model(feats, metas, 1)
+    bench.loss_fn(st, refs).backward()
+    opt.step(); opt.zero_grad(set_to_none=True)
+    for f in feats: f.grad = None
+
+for _ in range(3): step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+ev = [e for e in prof.key_averages() if e.device_time_total > 0 or getattr(e, "self_device_time_total", 0) > 0]
+rows = sorted(((e.self_device_time_total / 3.0, e.count / 3, e.key) for e in prof.key_averages() if e.self_device_time_total > 0), reverse=True)
+tot = sum(r[0] for r in rows)
+print(f"total device time per step: {tot/1e3:.3f} ms")
+for t, n, k in rows[:28]:
+    print(f"{t:9.1f} us {100*t/tot:5.1f}% n={n:6.1f} {k[:110]}")
