@@ -13,7 +13,7 @@ import threading
 
 from . import _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LEVELS = 8
 MODE_A, MODE_C, MODE_V2 = 0, 1, 2
 F32, BF16 = 0, 1
@@ -50,6 +50,7 @@ class XViewParams(C.Structure):
         ("attn_logits", C.c_void_p),
         ("offsets", C.c_void_p),
         ("cam_logits", C.c_void_p),
+        ("sched", C.c_void_p),
         ("out", C.c_void_p),
         ("wsum", C.c_void_p),
         ("mask", C.c_void_p),

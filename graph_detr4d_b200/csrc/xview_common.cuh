@@ -161,12 +161,33 @@ struct WarpCtx {
   float X0, Y0, Z0;  // reference point in metres
 };
 
-__device__ __forceinline__ bool warp_ctx(const gd4d_xview_params& p, WarpCtx& w) {
-  const int warp = threadIdx.x >> 5;
-  const long long gw = static_cast<long long>(blockIdx.x) * kWarpsPerCta + warp;
-  const long long total_warps = static_cast<long long>(p.B) * p.Q * p.Hh;
-  if (gw >= total_warps) return false;
+// Work distribution.  Static: warp gw = blockIdx*8 + warp handles item gw (one pass).
+// Dynamic (p.sched != NULL): persistent grid, every warp claims the next (b,q,head) item
+// from a global counter until none are left; the last warp to leave resets the counter.
+struct WorkIter {
+  long long total;
+  long long next;     // static mode: this warp's single item (or -1 when consumed)
+  bool dynamic;
+};
+
+__device__ __forceinline__ void work_begin(const gd4d_xview_params& p, WorkIter& it) {
+  it.total = static_cast<long long>(p.B) * p.Q * p.Hh;
+  it.dynamic = p.sched != nullptr;
+  it.next = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+}
+
+__device__ __forceinline__ bool work_next(const gd4d_xview_params& p, WorkIter& it, WarpCtx& w) {
+  long long gw;
   w.lane = threadIdx.x & 31;
+  if (it.dynamic) {
+    unsigned v = 0;
+    if (w.lane == 0) v = atomicAdd(p.sched, 1u);
+    gw = __shfl_sync(0xffffffffu, v, 0);
+  } else {
+    gw = it.next;
+    it.next = it.total;  // one item per warp
+  }
+  if (gw >= it.total) return false;
   w.h = static_cast<int>(gw % p.Hh);
   w.bq = static_cast<int>(gw / p.Hh);
   w.b = w.bq / p.Q;
@@ -176,6 +197,19 @@ __device__ __forceinline__ bool warp_ctx(const gd4d_xview_params& p, WarpCtx& w)
   w.Y0 = __fadd_rn(__fmul_rn(__ldg(rp + 1), p.pc_span[1]), p.pc_lo[1]);
   w.Z0 = __fadd_rn(__fmul_rn(__ldg(rp + 2), p.pc_span[2]), p.pc_lo[2]);
   return true;
+}
+
+__device__ __forceinline__ void work_end(const gd4d_xview_params& p, const WorkIter& it) {
+  if (!it.dynamic) return;
+  if ((threadIdx.x & 31) == 0) {
+    const unsigned warps = gridDim.x * kWarpsPerCta;
+    const unsigned done = atomicAdd(p.sched + 1, 1u);
+    if (done == warps - 1) {  // every warp has made its final (failing) claim: safe to reset
+      p.sched[0] = 0u;
+      p.sched[1] = 0u;
+      __threadfence();
+    }
+  }
 }
 
 // softmax over the head's L*P (<= 64) logits into sw[0..64) (zeros past L*P)

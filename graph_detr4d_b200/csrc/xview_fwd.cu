@@ -121,50 +121,56 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
   constexpr bool WIDE = (LANES == 32);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpCtx w;
-  if (!warp_ctx(p, w)) return;
   const int warp = threadIdx.x >> 5;
-  const int grp = w.lane / LANES;
-  const int sub = w.lane % LANES;
+  const int lane_ = threadIdx.x & 31;
+  const int grp = lane_ / LANES;
+  const int sub = lane_ % LANES;
   const size_t warp_bytes = sizeof(float) * kMaxLP + sizeof(Cand) * cand_cap;
   float* sw = reinterpret_cast<float*>(smem_raw + warp * warp_bytes);
   Cand* cands = reinterpret_cast<Cand*>(sw + kMaxLP);
 
-  if (MODE == GD4D_MODE_C) head_softmax(p, w, sw);
-  const int nvalid = build_candidates<MODE, Cand>(p, w, cands, p.mask != nullptr);
+  WorkIter wi;
+  work_begin(p, wi);
+  WarpCtx w;
+  while (work_next(p, wi, w)) {
+    if (MODE == GD4D_MODE_C) head_softmax(p, w, sw);
+    const int nvalid = build_candidates<MODE, Cand>(p, w, cands, p.mask != nullptr);
 
-  float acc[PL];
+    float acc[PL];
 #pragma unroll
-  for (int i = 0; i < PL; ++i) acc[i] = 0.f;
-  float wsum = 0.f;
-  const int total = nvalid * p.L;
-  for (int it0 = 0; it0 < total; it0 += 2 * GROUPS) {
-    ItemLoad<VT, NV> la, lb;
-    item_issue<MODE, VT, LANES, NV>(p, cands, sw, it0 + grp, total, w, sub, la);
-    item_issue<MODE, VT, LANES, NV>(p, cands, sw, it0 + GROUPS + grp, total, w, sub, lb);
-    item_pin<VT, NV>(la);
-    item_pin<VT, NV>(lb);
-    item_consume<VT, NV>(la, acc, wsum);
-    item_consume<VT, NV>(lb, acc, wsum);
-  }
+    for (int i = 0; i < PL; ++i) acc[i] = 0.f;
+    float wsum = 0.f;
+    const int total = nvalid * p.L;
+    for (int it0 = 0; it0 < total; it0 += 2 * GROUPS) {
+      ItemLoad<VT, NV> la, lb;
+      item_issue<MODE, VT, LANES, NV>(p, cands, sw, it0 + grp, total, w, sub, la);
+      item_issue<MODE, VT, LANES, NV>(p, cands, sw, it0 + GROUPS + grp, total, w, sub, lb);
+      item_pin<VT, NV>(la);
+      item_pin<VT, NV>(lb);
+      item_consume<VT, NV>(la, acc, wsum);
+      item_consume<VT, NV>(lb, acc, wsum);
+    }
 
-  // ---- reduce across lane groups, store ----------------------------------------------
+    // ---- reduce across lane groups, store ----------------------------------------------
 #pragma unroll
-  for (int o = LANES; o < 32; o <<= 1) {
+    for (int o = LANES; o < 32; o <<= 1) {
 #pragma unroll
-    for (int i = 0; i < PL; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+      for (int i = 0; i < PL; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if (grp == 0) {
+      float* o = WIDE ? p.out + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.C
+                      : p.out + static_cast<size_t>(w.bq) * p.C + w.h * kHeadDim;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4)
+          *reinterpret_cast<float4*>(o + (j * LANES + sub) * VEC + i) = make_float4(
+              acc[j * VEC + i], acc[j * VEC + i + 1], acc[j * VEC + i + 2], acc[j * VEC + i + 3]);
+    }
+    if (WIDE && p.wsum != nullptr && w.lane == 0) p.wsum[static_cast<size_t>(w.bq) * p.Hh + w.h] = wsum;
+    __syncwarp();  // the per-warp shared-memory lists are reused by the next work item
   }
-  if (grp == 0) {
-    float* o = WIDE ? p.out + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.C
-                    : p.out + static_cast<size_t>(w.bq) * p.C + w.h * kHeadDim;
-#pragma unroll
-    for (int j = 0; j < NV; ++j)
-#pragma unroll
-      for (int i = 0; i < VEC; i += 4)
-        *reinterpret_cast<float4*>(o + (j * LANES + sub) * VEC + i) =
-            make_float4(acc[j * VEC + i], acc[j * VEC + i + 1], acc[j * VEC + i + 2], acc[j * VEC + i + 3]);
-  }
-  if (WIDE && p.wsum != nullptr && w.lane == 0) p.wsum[static_cast<size_t>(w.bq) * p.Hh + w.h] = wsum;
+  work_end(p, wi);
 }
 
 template <int MODE, typename VT, int LANES, int NV>
@@ -174,7 +180,17 @@ static int launch_fwd(const gd4d_xview_params& p, const LaunchGeom& g, cudaStrea
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem);
     if (e != cudaSuccess) return GD4D_ERR_CUDA;
   }
-  kern<<<g.grid, g.block, g.smem, stream>>>(p, g.cand_cap);
+  int grid = g.grid;
+  if (p.sched != nullptr) {  // persistent grid: one resident wave, warps claim work dynamically
+    int dev = 0, sms = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, g.block, g.smem) != cudaSuccess)
+      return GD4D_ERR_CUDA;
+    const long long resident = static_cast<long long>(sms) * (occ > 0 ? occ : 1);
+    if (resident < grid) grid = static_cast<int>(resident);
+  }
+  kern<<<grid, g.block, g.smem, stream>>>(p, g.cand_cap);
   return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
 }
 

@@ -20,6 +20,7 @@ __all__ = ["XViewConfig", "pack_features", "PackedFeatures", "xview_forward", "x
            "xview_attention", "lidar2img_to_tensor", "prepare_forward", "prepare_backward",
            "launch_count", "MODE_A", "MODE_C", "MODE_V2"]
 
+DYNAMIC_SCHEDULE = True   # persistent grid + work counter (False: one warp per item, static)
 _LAUNCHES = 0      # kernels of libgd4d_xview.so launched by this process (bench: gpu_launches)
 
 
@@ -42,6 +43,22 @@ def _dtype_code(t: torch.Tensor) -> int:
 
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+_SCHED = {}
+
+
+def _sched_ptr(device) -> int:
+    """Per-(device, stream) 2-word work counter for the persistent-grid scheduler.  Zeroed
+    once; the kernels reset it themselves, so launches that share it must be ordered on one
+    stream -- which is why it is keyed by the current stream."""
+    key = (torch.device(device).index, _stream_ptr(device))
+    t = _SCHED.get(key)
+    if t is None:
+        with torch.no_grad():
+            t = torch.zeros(2, dtype=torch.int32, device=device)
+        _SCHED[key] = t
+    return t.data_ptr()
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -247,6 +264,9 @@ def _fill_params(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: in
     p.attn_logits = attn_logits.data_ptr()
     p.offsets = offsets.data_ptr() if offsets is not None else None
     p.cam_logits = cam_logits.data_ptr() if cam_logits is not None else None
+    if DYNAMIC_SCHEDULE and cfg.mode == MODE_C:
+        # mode A launches are ~10 us of work: the per-item claim costs more than the tail it removes
+        p.sched = _sched_ptr(ref.device)
     return p
 
 

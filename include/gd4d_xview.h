@@ -40,7 +40,7 @@ extern "C" {
 #define GD4D_API
 #endif
 
-#define GD4D_ABI_VERSION 2
+#define GD4D_ABI_VERSION 3
 #define GD4D_MAX_LEVELS 8
 
 typedef enum gd4d_status {
@@ -120,6 +120,11 @@ typedef struct gd4d_xview_params {
   const float* attn_logits;
   const float* offsets;
   const float* cam_logits;
+  uint32_t* sched;              /* optional: 2 uint32, zeroed ONCE by the caller.  When set the
+                                   kernels run a persistent grid whose warps claim (b,q,head)
+                                   work items from this counter (no wave-quantisation tail) and
+                                   the last warp to finish resets it, so it is reusable by the
+                                   next launch ON THE SAME STREAM without another memset.       */
   float* out;
   float* wsum;                  /* wide only */
   uint8_t* mask;

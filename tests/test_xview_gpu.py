@@ -238,3 +238,30 @@ def test_grad_sink_is_shared_across_layers():
     tot_o.backward()
     for fg, fo in zip(feats_g, feats_o):
         assert H.rel_err(fg.grad.cpu(), fo.grad) <= GRAD_TOL
+
+
+def test_dynamic_and_static_schedules_agree_and_counter_resets():
+    sc = H.scene(B=2, T=2, Q=333)
+    logits, offsets, cam = H.rand_inputs_c(sc)
+    packed = _pack(sc["feats"])
+    cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=True)
+    args = (cfg, packed.levels, 2, sc["N"], sc["ref"].cuda(), logits.cuda(), offsets.cuda(), cam.cuda(),
+            sc["l2i"].cuda())
+    outs = {}
+    for dyn in (True, False):
+        ops.DYNAMIC_SCHEDULE = dyn
+        try:
+            for rep in range(3):                    # repeated launches reuse the self-resetting counter
+                (o, ws), _ = ops.xview_forward(*args)
+            gv = [torch.zeros(v.shape, device="cuda") for v in packed.levels]
+            g = ops.xview_backward(*args, torch.ones_like(o), gv, grad_wsum=torch.ones_like(ws))
+            outs[dyn] = (o, ws, gv, g)
+        finally:
+            ops.DYNAMIC_SCHEDULE = True
+    torch.cuda.synchronize()
+    for t in ops._SCHED.values():
+        assert int(t.abs().sum()) == 0              # every launch left the counter at zero
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    for a, b in zip(outs[True][2], outs[False][2]):
+        assert H.rel_err(a, b) <= 1e-5              # atomics: order differs, values agree
+    assert H.rel_err(outs[True][3][0], outs[False][3][0]) <= 1e-5

@@ -40,7 +40,13 @@ for name, mode, T, dtype in [("C_T1_fp32", MODE_C, 1, torch.float32), ("C_T2_fp3
     if isinstance(out, tuple): out = out[0]
     gout = torch.randn_like(out)
     gvals = [torch.zeros(v.shape, device='cuda', dtype=torch.float32) for v in packed.levels]
-    bwd = lambda: ops.xview_backward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i, gout, gvals)
+    if "--static" in _s.argv: ops.DYNAMIC_SCHEDULE = False
+    fprep = ops.prepare_forward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i)
+    fwd = fprep.launch
+    bprep = ops.prepare_backward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i, gout, gvals)
+    bwd = bprep.launch
+    if "--no-gv" in _s.argv:
+        for l in range(len(gvals)): bprep.params.grad_value[l] = None
     feats_gpu = [f.cuda() for f in sc["feats"]]
     pk = lambda: ops.pack_features(feats_gpu, dtype)
     res[name] = dict(valid_frac=float(mask.float().mean()),
