@@ -5,7 +5,7 @@ attention for Graph-DETR4D, behind the reference's mmcv ATTENTION module API.
 a hyphen cannot appear in a Python package name.)
 """
 from . import _lib, ops, synthetic  # noqa: F401
-from .modules import (ATTENTION, Deform3DCrossAttn, Detr3DCrossAtten, build_attention,  # noqa: F401
+from .modules import (ATTENTION, Deform3DCrossAttn, Detr3DCrossAtten, Detr3DCrossAttenV2, build_attention,  # noqa: F401
                       clear_caches, inverse_sigmoid, lidar2img_device)
 from .ops import (MODE_A, MODE_C, PackedFeatures, XViewConfig, pack_features,  # noqa: F401
                   xview_attention, xview_backward, xview_forward)

@@ -5,6 +5,7 @@
 namespace gd4d {
 int dispatch_forward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
 int dispatch_backward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
+int dispatch_v2(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream, bool backward);
 int dispatch_pack(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t images, int C,
                   int H, int W, cudaStream_t stream);
 
@@ -13,7 +14,8 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 static int validate(const gd4d_xview_params* p, bool backward, LaunchGeom* g) {
   if (p == nullptr) return GD4D_ERR_NULL;
   if (p->abi_version != GD4D_ABI_VERSION) return GD4D_ERR_UNSUPPORTED;
-  if (p->mode != GD4D_MODE_A && p->mode != GD4D_MODE_C) return GD4D_ERR_UNSUPPORTED;
+  if (p->mode != GD4D_MODE_A && p->mode != GD4D_MODE_C && p->mode != GD4D_MODE_V2)
+    return GD4D_ERR_UNSUPPORTED;
   if (p->value_dtype != GD4D_F32 && p->value_dtype != GD4D_BF16) return GD4D_ERR_UNSUPPORTED;
   if (p->B <= 0 || p->Q <= 0 || p->N <= 0 || p->Hh <= 0 || p->L <= 0 || p->P <= 0 || p->C <= 0)
     return GD4D_ERR_DIMS;
@@ -40,6 +42,11 @@ static int validate(const gd4d_xview_params* p, bool backward, LaunchGeom* g) {
     if (p->offsets == nullptr || p->cam_logits == nullptr) return GD4D_ERR_NULL;
     if (p->L * p->P > kMaxLP) return GD4D_ERR_UNSUPPORTED;
   }
+  if (p->mode == GD4D_MODE_V2) {
+    if (p->offsets == nullptr) return GD4D_ERR_NULL;
+    // the reference multiplies (..,L,P) weights with (..,P,L) samples: only L == P runs
+    if (p->L != p->P || p->L * p->P > kMaxLP) return GD4D_ERR_UNSUPPORTED;
+  }
   if (backward) {
     if (p->grad_out == nullptr) return GD4D_ERR_NULL;
     if (!aligned16(p->grad_out)) return GD4D_ERR_ALIGN;
@@ -53,8 +60,9 @@ static int validate(const gd4d_xview_params* p, bool backward, LaunchGeom* g) {
   const int pp = p->mode == GD4D_MODE_C ? p->P : 1;
   const long long cand_cap = static_cast<long long>(p->N) * pp;
   // backward keeps 16 more bytes per candidate (coordinate-gradient accumulators)
-  const long long per_cand = backward ? 32 : 16;
-  const long long per_warp = sizeof(float) * kMaxLP * (backward ? 5 : 1) + per_cand * cand_cap;
+  const bool big = backward || p->mode == GD4D_MODE_V2;   // V2 uses the backward layout both ways
+  const long long per_cand = big ? 32 : 16;
+  const long long per_warp = sizeof(float) * kMaxLP * (big ? 5 : 1) + per_cand * cand_cap;
   const long long smem = per_warp * kWarpsPerCta;
   if (smem > 200 * 1024) return GD4D_ERR_UNSUPPORTED;
   g->grid = static_cast<int>(ctas);
@@ -99,6 +107,8 @@ int gd4d_xview_forward(const gd4d_xview_params* p, void* cuda_stream) {
   gd4d::LaunchGeom g{};
   const int st = gd4d::validate(p, false, &g);
   if (st != GD4D_OK) return st;
+  if (p->mode == GD4D_MODE_V2)
+    return gd4d::dispatch_v2(*p, g, static_cast<cudaStream_t>(cuda_stream), false);
   return gd4d::dispatch_forward(*p, g, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -106,6 +116,8 @@ int gd4d_xview_backward(const gd4d_xview_params* p, void* cuda_stream) {
   gd4d::LaunchGeom g{};
   const int st = gd4d::validate(p, true, &g);
   if (st != GD4D_OK) return st;
+  if (p->mode == GD4D_MODE_V2)
+    return gd4d::dispatch_v2(*p, g, static_cast<cudaStream_t>(cuda_stream), true);
   return gd4d::dispatch_backward(*p, g, static_cast<cudaStream_t>(cuda_stream));
 }
 

@@ -5,6 +5,7 @@ fused sm_100a kernels.
 
   Detr3DCrossAtten   <- projects/mmdet3d_plugin/models/utils/detr3d_transformer.py:229-390
   Deform3DCrossAttn  <- projects/mmdet3d_plugin/models/utils/deform3d_cross_attn.py:33-339
+  Detr3DCrossAttenV2 <- projects/mmdet3d_plugin/models/utils/detr3d_transformer.py:441-709
 
 What stays in torch (cuBLAS library GEMMs, tiny): the weight/offset generator
 Linears, value_proj, output_proj, position_encoder.  What moved into ONE kernel
@@ -48,7 +49,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .glue import fast_linear
-from .ops import MODE_A, MODE_C, PackedFeatures, XViewConfig
+from .ops import MODE_A, MODE_C, MODE_V2, PackedFeatures, XViewConfig
 
 import sys as _sys
 
@@ -302,6 +303,82 @@ class Detr3DCrossAtten(BaseModule):
         cfg = XViewConfig(MODE_A, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w)
         l2i = _L2I_CACHE.get(img_metas, query.device)
         out = ops.xview_attention(cfg, packed, reference_points, logits, lidar2img=l2i)   # (B,Q,C)
+        out = fast_linear(out.permute(1, 0, 2), self.output_proj)
+        pos_feat = _run_position_encoder(self.position_encoder, inverse_sigmoid(reference_points)).permute(1, 0, 2)
+        return self.dropout(out) + inp_residual + pos_feat
+
+
+# ----------------------------------------------------------------------------------------
+# variant V2 (registered by the reference, used by no config)
+# ----------------------------------------------------------------------------------------
+@ATTENTION.register_module()
+class Detr3DCrossAttenV2(BaseModule):
+    """Deformable-DETR style 2D offsets around the projected centre
+    (detr3d_transformer.py:441-709).  Like the reference it needs
+    num_points == num_levels and batch size 1."""
+
+    def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=5, num_cams=6,
+                 im2col_step=64, pc_range=None, dropout=0.1, norm_cfg=None, init_cfg=None,
+                 batch_first=False, feature_dtype=None):
+        super().__init__(init_cfg)
+        if embed_dims % num_heads != 0:
+            raise ValueError(f"embed_dims must be divisible by num_heads, "
+                             f"but got {embed_dims} and {num_heads}")
+        if not _is_power_of_2(embed_dims // num_heads):
+            warnings.warn("You'd better set embed_dims in MultiScaleDeformAttention to make the "
+                          "dimension of each attention head a power of 2 which is more efficient "
+                          "in our CUDA implementation.")
+        self.norm_cfg = norm_cfg
+        self.init_cfg = init_cfg
+        self.dropout = nn.Dropout(dropout)
+        self.pc_range = pc_range
+        self.im2col_step = im2col_step
+        self.embed_dims = embed_dims
+        self.num_levels = num_levels
+        self.num_heads = num_heads
+        self.num_points = num_points
+        self.num_cams = num_cams
+        self.attention_weights = nn.Linear(embed_dims, num_cams * num_heads * num_levels * num_points)
+        self.sampling_offsets = nn.Linear(embed_dims, num_cams * num_heads * num_levels * num_points * 2)
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.position_encoder = _position_encoder(3, embed_dims)
+        self.batch_first = batch_first
+        self.feature_dtype = _feature_dtype(feature_dtype)
+        self.init_weight()
+
+    def init_weight(self):
+        _constant_(self.sampling_offsets, 0.0)
+        thetas = torch.arange(self.num_heads, dtype=torch.float32) * (2.0 * math.pi / self.num_heads)
+        grid_init = torch.stack([thetas.cos(), thetas.sin()], -1)
+        grid_init = (grid_init / grid_init.abs().max(-1, keepdim=True)[0]).view(
+            1, self.num_heads, 1, 1, 2).repeat(self.num_cams, 1, self.num_levels, self.num_points, 1)
+        for i in range(self.num_points):
+            grid_init[:, :, :, i, :] *= i + 1
+        self.sampling_offsets.bias.data = grid_init.view(-1)
+        _constant_(self.attention_weights, 0.0, 0.0)
+        _xavier_uniform_(self.output_proj, 0.0)
+
+    def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
+                reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        inp_residual = query if residual is None else residual
+        if query_pos is not None:
+            query = query + query_pos
+        query = query.permute(1, 0, 2)
+        img_metas = kwargs["img_metas"]
+        packed = _get_packed(value, self.feature_dtype)
+        if packed.B != 1:
+            raise ValueError("Detr3DCrossAttenV2 broadcasts (B*N) against N: batch size must be 1 "
+                             "(detr3d_transformer.py:700)")
+        logits = fast_linear(query, self.attention_weights)      # (B,Q,N*Hh*L*P)
+        offsets = fast_linear(query, self.sampling_offsets)      # (B,Q,N*Hh*L*P*2)
+        img_h, img_w = _img_hw(img_metas)
+        cfg = XViewConfig(MODE_V2, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w)
+        l2i = _L2I_CACHE.get(img_metas, query.device)
+        out = ops.xview_attention(cfg, packed, reference_points, logits, offsets, None, l2i)   # (B,Q,C)
         out = fast_linear(out.permute(1, 0, 2), self.output_proj)
         pos_feat = _run_position_encoder(self.position_encoder, inverse_sigmoid(reference_points)).permute(1, 0, 2)
         return self.dropout(out) + inp_residual + pos_feat

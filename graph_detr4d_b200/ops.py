@@ -279,6 +279,13 @@ def _check_shapes(cfg, B, N, L, ref, attn_logits, offsets, cam_logits, lidar2img
     P = cfg.num_points
     if cfg.mode == MODE_A:
         want = B * Q * N * P * L
+    elif cfg.mode == MODE_V2:
+        want = B * Q * N * cfg.num_heads * L * P
+        if offsets is None or offsets.numel() != want * 2:
+            raise ValueError("V2 offsets must hold B*Q*N*Hh*L*P*2 values")
+        if L != P:
+            raise ValueError("Detr3DCrossAttenV2 semantics need num_points == num_levels "
+                             "(detr3d_transformer.py:611 vs :709)")
     else:
         want = B * Q * cfg.num_heads * L * P
         if offsets is None or offsets.numel() != B * Q * cfg.num_heads * P * 3:

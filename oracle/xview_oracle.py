@@ -291,6 +291,21 @@ def detr3d_cross_atten_forward(sd, query, value, query_pos, reference_points, im
     return out + inp_residual + pos
 
 
+def detr3d_cross_atten_v2_forward(sd, query, value, query_pos, reference_points, img_metas, pc_range,
+                                  num_heads):
+    """Detr3DCrossAttenV2.forward, eval mode (detr3d_transformer.py:542-633)."""
+    inp_residual = query
+    q = (query + query_pos).permute(1, 0, 2)
+    logits = _lin(sd, "attention_weights", q)
+    offsets = _lin(sd, "sampling_offsets", q)
+    l2i = lidar2img_tensor(img_metas, reference_points)
+    img_h, img_w = img_metas[0]["img_shape"][0][0], img_metas[0]["img_shape"][0][1]
+    out, _ = xview_v2_core(value, reference_points, offsets, logits, l2i, pc_range, img_h, img_w, num_heads)
+    out = _lin(sd, "output_proj", out.permute(1, 0, 2))
+    pos = _position_encoder(sd, inverse_sigmoid(reference_points.clone())).permute(1, 0, 2)
+    return out + inp_residual + pos
+
+
 def deform3d_cross_attn_forward(sd, query, value, query_pos, reference_points, img_metas,
                                 pc_range, num_heads, depth_encode=False):
     """Deform3DCrossAttn.forward, eval mode (deform3d_cross_attn.py:152-339)."""

@@ -31,7 +31,7 @@ def bf16_bits(t):
 
 def run(variant):
     ref = ref_loader.load()
-    T = 1 if variant == "A" else 2
+    T = 2 if variant == "C" else 1
     N = 6 * T
     feats = [f.to(torch.bfloat16).float() for f in syn.make_feats(1, N, C, SHAPES, seed=11)]
     query, query_pos, rp = syn.make_queries(1, Q, C, seed=12)
@@ -40,6 +40,9 @@ def run(variant):
     if variant == "A":
         mod = ref.Detr3DCrossAtten(embed_dims=C, num_heads=HEADS, num_levels=4, num_points=1, num_cams=N,
                                    pc_range=syn.PC_RANGE, dropout=0.1)
+    elif variant == "V2":
+        mod = ref.Detr3DCrossAttenV2(embed_dims=C, num_heads=HEADS, num_levels=4, num_points=4, num_cams=N,
+                                     pc_range=syn.PC_RANGE, dropout=0.1)
     else:
         mod = ref.Deform3DCrossAttnCPU(embed_dims=C, num_heads=HEADS, num_levels=4, num_points=4,
                                        num_cams=N, pc_range=syn.PC_RANGE, dropout=0.1)
@@ -75,5 +78,6 @@ def run(variant):
 if __name__ == "__main__":
     import warnings
     warnings.filterwarnings("ignore")
-    run("A")
-    run("C")
+    only = sys.argv[1:] or ["A", "C", "V2"]
+    for v in only:
+        run(v)

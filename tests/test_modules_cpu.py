@@ -12,7 +12,7 @@ from tests.test_oracle_golden import load_golden
 
 
 def test_registry_builds_by_type_name():
-    for name in ("Detr3DCrossAtten", "Deform3DCrossAttn"):
+    for name in ("Detr3DCrossAtten", "Deform3DCrossAttn", "Detr3DCrossAttenV2"):
         assert g.ATTENTION.get(name) is not None
     m = g.build_attention(dict(type="Deform3DCrossAttn", embed_dims=256, num_heads=8, num_levels=4,
                                num_points=4, num_cams=12, pc_range=syn.PC_RANGE, dropout=0.1,
@@ -30,11 +30,12 @@ def test_constructor_errors_and_warnings():
 def test_forward_signature_matches_reference_contract():
     want = ["query", "key", "value", "residual", "query_pos", "key_padding_mask", "reference_points",
             "spatial_shapes", "level_start_index", "kwargs"]
-    for cls in (g.Detr3DCrossAtten, g.Deform3DCrossAttn):
+    for cls in (g.Detr3DCrossAtten, g.Deform3DCrossAttn, g.Detr3DCrossAttenV2):
         assert list(inspect.signature(cls.forward).parameters)[1:] == want
 
 
-@pytest.mark.parametrize("variant,cls", [("A", "Detr3DCrossAtten"), ("C", "Deform3DCrossAttn")])
+@pytest.mark.parametrize("variant,cls", [("A", "Detr3DCrossAtten"), ("C", "Deform3DCrossAttn"),
+                                         ("V2", "Detr3DCrossAttenV2")])
 def test_golden_state_dict_loads_strictly(variant, cls):
     gd = load_golden(variant)
     N = 6 * gd["T"]

@@ -12,7 +12,8 @@ from tests.test_oracle_golden import load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant,cls", [("A", "Detr3DCrossAtten"), ("C", "Deform3DCrossAttn")])
+@pytest.mark.parametrize("variant,cls", [("A", "Detr3DCrossAtten"), ("C", "Deform3DCrossAttn"),
+                                         ("V2", "Detr3DCrossAttenV2")])
 def test_module_matches_reference_golden(variant, cls):
     gd = load_golden(variant)
     N = 6 * gd["T"]

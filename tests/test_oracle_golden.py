@@ -33,7 +33,7 @@ def load_golden(variant):
                 grad_feats=[t(f"grad_feat{j}") for j in range(i)])
 
 
-@pytest.mark.parametrize("variant", ["A", "C"])
+@pytest.mark.parametrize("variant", ["A", "C", "V2"])
 def test_oracle_reproduces_golden(variant):
     gd = load_golden(variant)
     feats = [f.clone().requires_grad_(True) for f in gd["feats"]]
@@ -41,6 +41,9 @@ def test_oracle_reproduces_golden(variant):
     rp = gd["ref"].clone().requires_grad_(True)
     if variant == "A":
         y = xo.detr3d_cross_atten_forward(gd["sd"], q, feats, gd["query_pos"], rp, gd["metas"], syn.PC_RANGE)
+    elif variant == "V2":
+        y = xo.detr3d_cross_atten_v2_forward(gd["sd"], q, feats, gd["query_pos"], rp, gd["metas"],
+                                             syn.PC_RANGE, num_heads=2)
     else:
         y = xo.deform3d_cross_attn_forward(gd["sd"], q, feats, gd["query_pos"], rp, gd["metas"],
                                            syn.PC_RANGE, num_heads=2)

@@ -96,6 +96,32 @@ def test_variant_c_module(ref, T, P):
         assert H.rel_err(a.grad, b.grad) <= 1e-5
 
 
+def test_variant_v2_module(ref):
+    sc = H.scene(B=1, T=1, Q=90)
+    torch.manual_seed(5)
+    mod = ref.Detr3DCrossAttenV2(num_cams=6, num_points=4, pc_range=syn.PC_RANGE).eval()
+    syn.randomize_generators(mod)
+    feats = [f.clone().requires_grad_(True) for f in sc["feats"]]
+    rp = sc["ref"].clone().requires_grad_(True)
+    y_ref = mod(sc["query"], None, feats, query_pos=sc["query_pos"], reference_points=rp, img_metas=sc["metas"])
+    g = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(1))
+    (y_ref * g).sum().backward()
+    feats2 = [f.clone().requires_grad_(True) for f in sc["feats"]]
+    rp2 = sc["ref"].clone().requires_grad_(True)
+    y = xo.detr3d_cross_atten_v2_forward(mod.state_dict(), sc["query"], feats2, sc["query_pos"], rp2,
+                                         sc["metas"], syn.PC_RANGE, 8)
+    (y * g).sum().backward()
+    assert H.rel_err(y, y_ref) <= 2e-6
+    assert H.rel_err(rp2.grad, rp.grad) <= 1e-5
+    for a, b in zip(feats2, feats):
+        assert H.rel_err(a.grad, b.grad) <= 1e-5
+    # the reference cannot run V2 unless num_points == num_levels (weights (L,P) x samples (P,L))
+    bad = ref.Detr3DCrossAttenV2(num_cams=6, num_points=5, pc_range=syn.PC_RANGE).eval()
+    with pytest.raises(RuntimeError):
+        bad(sc["query"], None, sc["feats"], query_pos=sc["query_pos"], reference_points=sc["ref"],
+            img_metas=sc["metas"])
+
+
 def test_shipped_cpu_branch_is_broken_and_patch_is_one_token(ref):
     """deform3d_cross_attn.py:305-309: documents why the oracle needs the substitution."""
     sc = H.scene(B=1, T=1, Q=8)

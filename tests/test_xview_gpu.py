@@ -265,3 +265,37 @@ def test_dynamic_and_static_schedules_agree_and_counter_resets():
     for a, b in zip(outs[True][2], outs[False][2]):
         assert H.rel_err(a, b) <= 1e-5              # atomics: order differs, values agree
     assert H.rel_err(outs[True][3][0], outs[False][3][0]) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# mode V2 (Detr3DCrossAttenV2)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,Q,dtype", [(1, 70, torch.float32), (2, 33, torch.float32), (1, 40, torch.bfloat16)])
+def test_mode_v2_forward_backward(T, Q, dtype):
+    from graph_detr4d_b200.ops import MODE_V2
+    sc = H.scene(B=1, T=T, Q=Q)
+    N, Hh, L, P = sc["N"], 8, 4, 4
+    g = torch.Generator().manual_seed(12)
+    logits = torch.randn(1, Q, N * Hh * L * P, generator=g)
+    offsets = torch.randn(1, Q, N * Hh * L * P * 2, generator=g) * 3.0
+    gout = torch.randn(1, Q, sc["C"], generator=g)
+    feats_src = [f.to(dtype).float() for f in sc["feats"]]
+    feats_o = [_leaf(f) for f in feats_src]
+    ref_o, log_o, off_o = _leaf(sc["ref"]), _leaf(logits), _leaf(offsets)
+    out_o, mask_o = xo.xview_v2_core(feats_o, ref_o, off_o, log_o, sc["l2i"], syn.PC_RANGE, 900, 1600, Hh)
+    out_o.backward(gout)
+    feats_g = [_leaf(f.cuda()) for f in feats_src]
+    ref_g, log_g, off_g = (_leaf(t.cuda()) for t in (sc["ref"], logits, offsets))
+    packed = ops.pack_features(feats_g, dtype)
+    cfg = XViewConfig(MODE_V2, Hh, P, tuple(syn.PC_RANGE), 900.0, 1600.0)
+    out = ops.xview_attention(cfg, packed, ref_g, log_g, off_g, None, sc["l2i"].cuda())
+    out.backward(gout.cuda())
+    _, mask = ops.xview_forward(cfg, packed.levels, 1, N, sc["ref"].cuda(), logits.cuda(), offsets.cuda(),
+                                None, sc["l2i"].cuda(), want_mask=True)
+    assert torch.equal(mask.cpu().bool(), mask_o)
+    assert H.rel_err(out.detach().cpu(), out_o.detach()) <= FWD_TOL
+    assert H.rel_err(log_g.grad.cpu(), log_o.grad) <= GRAD_TOL
+    assert H.rel_err(off_g.grad.cpu(), off_o.grad) <= GRAD_TOL
+    assert H.rel_err(ref_g.grad.cpu(), ref_o.grad) <= GRAD_TOL
+    for fg, fo in zip(feats_g, feats_o):
+        assert H.rel_err(fg.grad.cpu(), fo.grad) <= GRAD_TOL
