@@ -100,6 +100,15 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p, bool pred) {
   return t;
 }
 
+// unpredicated variant: the caller guarantees a valid address (clamped corners + zero weight)
+__device__ __forceinline__ uint4 ldg_nc_v4_all(const char* p) {
+  uint4 t;
+  asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+               : "l"(p));
+  return t;
+}
+
 __device__ __forceinline__ void pin(uint4& a, uint4& b, uint4& c, uint4& d) {
   asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z),
                     "+r"(b.w), "+r"(c.x), "+r"(c.y), "+r"(c.z), "+r"(c.w), "+r"(d.x), "+r"(d.y),

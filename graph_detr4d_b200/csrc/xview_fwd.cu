@@ -1,17 +1,26 @@
 // Fused project -> mask -> bilinear-sample -> weight -> reduce forward kernel.
 //
-// One warp per (batch b, query q, head h).  Phase 1: the 32 lanes project the
-// warp's N*P candidate points (camera n, graph-offset point p) in parallel and
-// ballot-compact the valid ones into a per-warp shared-memory list.  Phase 2:
-// the warp walks (valid candidate, level) items.  A lane GROUP owns one item and
-// covers its channel slice with 16-byte loads:
-//   narrow (mmcv layout, value already projected, 32-ch head slice):
-//       fp32 8 lanes x 1 vector, bf16 4 lanes x 1 vector -> 4 / 8 items per warp-wide load
-//   wide   (gather-then-project, all C channels of the raw maps per head):
-//       32 lanes x NV vectors (fp32 C=256: NV=2, bf16 C=256: NV=1) -> 1 item per NV loads
-// so every warp-wide load instruction fetches whole 64..512-byte runs, fully
-// coalesced, and two items per group are kept in flight.  fp32 accumulation in
-// registers, a shuffle reduce across groups, coalesced 16-byte stores.
+// One warp per (batch b, query q, head h) work item (claimed dynamically from a
+// persistent grid when p.sched is set).  Three phases, all warp-synchronous:
+//
+//  1. candidates  the 32 lanes project the warp's N*P candidate points (camera n,
+//                 graph-offset point p) in parallel, in the reference's exact op order
+//                 (bit-exact mask), and ballot-compact the valid ones (~18 %) into a
+//                 per-warp shared-memory list.
+//  2. records     the (valid candidate, level) items are turned, 32 at a time and ONE
+//                 LANE PER ITEM, into 48-byte records {4 corner pointers, 4 weights}.
+//                 Out-of-map corners keep a valid (clamped) pointer and get weight 0,
+//                 so the gather needs no predicates and no zero-fill.  (r1 finding: with
+//                 every lane redoing the per-item scalar math the kernel issued ~220
+//                 warp-instructions per item and was ISSUE-bound at 60 % issue-active;
+//                 records cut that to ~60.)
+//  3. gather      a lane GROUP owns an item and covers its channel run with 16-byte
+//                 loads: narrow (mmcv layout, projected value, 32-ch head slice) 8 lanes
+//                 fp32 / 4 lanes bf16; wide (gather-then-project, all C raw channels per
+//                 head) 32 lanes x NV vectors.  16 independent 16-byte gathers per lane
+//                 are issued back-to-back (volatile PTX + register pin + launch bounds)
+//                 before the first FMA consumes one.  fp32 accumulate in registers, a
+//                 shuffle reduce across groups, coalesced 16-byte stores.
 //
 // Replaces (reference, projects/mmdet3d_plugin/models/utils/):
 //   mode A  detr3d_transformer.py:376-383 + feature_sampling :397-438
@@ -31,19 +40,20 @@ struct __align__(16) Cand {
   }
 };
 
-template <typename VT, int NV>
-struct ItemLoad {
-  static constexpr int PL = Slice<VT>::VEC * NV;  // channels per lane
-  uint4 r00[NV], r01[NV], r10[NV], r11[NV];       // raw 16-byte corner runs
-  float w00, w01, w10, w11, wt, inb;
+// gather record of one (candidate, level) item
+struct __align__(16) RecF {
+  const char* p00;
+  const char* p01;
+  const char* p10;
+  const char* p11;
+  float w00, w01, w10, w11;  // bilinear weight * attention weight; 0 when out of the map
 };
 
-template <int MODE, typename VT, int LANES, int NV>
-__device__ __forceinline__ void item_issue(const gd4d_xview_params& p, const Cand* cands,
-                                           const float* sw, int item, int total, const WarpCtx& w,
-                                           int sub, ItemLoad<VT, NV>& ld) {
-  constexpr int VEC = Slice<VT>::VEC;
-  constexpr bool WIDE = (LANES == 32);
+template <int MODE, typename VT, bool WIDE>
+__device__ __forceinline__ RecF build_record(const gd4d_xview_params& p, const Cand* cands,
+                                             const float* sw, int item, int total, const WarpCtx& w,
+                                             float& wsum_lane) {
+  RecF r;
   const bool active = item < total;
   const int it = active ? item : 0;
   const int k = it / p.L;
@@ -59,75 +69,51 @@ __device__ __forceinline__ void item_issue(const gd4d_xview_params& p, const Can
     wt = 0.f;
     for (int pp = 0; pp < p.P; ++pp) wt += sigmoidf_(__ldg(a + pp * p.L));
   }
+  if (!active) wt = 0.f;
   const int W = p.level_w[l], H = p.level_h[l];
   const float ix = to_pixel(to_grid<MODE>(c.u), static_cast<float>(W));
   const float iy = to_pixel(to_grid<MODE>(c.v), static_cast<float>(H));
   const Footprint f = footprint(ix, iy, W, H);
-  ld.w00 = (1.f - f.tx) * (1.f - f.ty);
-  ld.w01 = f.tx * (1.f - f.ty);
-  ld.w10 = (1.f - f.tx) * f.ty;
-  ld.w11 = f.tx * f.ty;
-  ld.wt = active ? wt : 0.f;
-  ld.inb = (f.in00 ? ld.w00 : 0.f) + (f.in01 ? ld.w01 : 0.f) + (f.in10 ? ld.w10 : 0.f) +
-           (f.in11 ? ld.w11 : 0.f);
-  const VT* base = static_cast<const VT*>(p.value[l]);
+  const float b00 = (1.f - f.tx) * (1.f - f.ty), b01 = f.tx * (1.f - f.ty);
+  const float b10 = (1.f - f.tx) * f.ty, b11 = f.tx * f.ty;
+  const float i00 = f.in00 ? b00 : 0.f, i01 = f.in01 ? b01 : 0.f;
+  const float i10 = f.in10 ? b10 : 0.f, i11 = f.in11 ? b11 : 0.f;
+  r.w00 = wt * i00; r.w01 = wt * i01; r.w10 = wt * i10; r.w11 = wt * i11;
+  wsum_lane = fmaf(wt, (i00 + i01) + (i10 + i11), wsum_lane);
+  // clamped corner coordinates: always a valid address, weight is already 0 if outside
+  const int x0 = min(max(f.x0, 0), W - 1), x1 = min(max(f.x0 + 1, 0), W - 1);
+  const int y0 = min(max(f.y0, 0), H - 1), y1 = min(max(f.y0 + 1, 0), H - 1);
   const size_t img = static_cast<size_t>(w.b) * p.N + n;
-  const size_t row0 = (img * H + f.y0) * W;
-  const size_t choff = (WIDE ? 0 : static_cast<size_t>(w.h) * kHeadDim) + sub * VEC;
-  const VT* p00 = base + (row0 + f.x0) * p.C + choff;
-  const VT* p10 = p00 + static_cast<size_t>(W) * p.C;
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int o = j * LANES * VEC;
-    ld.r00[j] = ldg_nc_v4(p00 + o, active & f.in00);
-    ld.r01[j] = ldg_nc_v4(p00 + p.C + o, active & f.in01);
-    ld.r10[j] = ldg_nc_v4(p10 + o, active & f.in10);
-    ld.r11[j] = ldg_nc_v4(p10 + p.C + o, active & f.in11);
-  }
-}
-
-template <typename VT, int NV>
-__device__ __forceinline__ void item_pin(ItemLoad<VT, NV>& ld) {
-#pragma unroll
-  for (int j = 0; j < NV; ++j) pin(ld.r00[j], ld.r01[j], ld.r10[j], ld.r11[j]);
-}
-
-template <typename VT, int NV>
-__device__ __forceinline__ void item_consume(const ItemLoad<VT, NV>& ld,
-                                             float (&acc)[ItemLoad<VT, NV>::PL], float& wsum) {
-  constexpr int VEC = Slice<VT>::VEC;
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    float c00[VEC], c01[VEC], c10[VEC], c11[VEC];
-    Slice<VT>::unpack(ld.r00[j], c00);
-    Slice<VT>::unpack(ld.r01[j], c01);
-    Slice<VT>::unpack(ld.r10[j], c10);
-    Slice<VT>::unpack(ld.r11[j], c11);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float s = ld.w00 * c00[i] + ld.w01 * c01[i] + ld.w10 * c10[i] + ld.w11 * c11[i];
-      acc[j * VEC + i] = fmaf(ld.wt, s, acc[j * VEC + i]);
-    }
-  }
-  wsum = fmaf(ld.wt, ld.inb, wsum);
+  const size_t rowb = static_cast<size_t>(p.C) * sizeof(VT);
+  const char* base = static_cast<const char*>(p.value[l]) + img * H * W * rowb +
+                     (WIDE ? 0 : static_cast<size_t>(w.h) * kHeadDim * sizeof(VT));
+  const size_t r0 = static_cast<size_t>(y0) * W, r1 = static_cast<size_t>(y1) * W;
+  r.p00 = base + (r0 + x0) * rowb;
+  r.p01 = base + (r0 + x1) * rowb;
+  r.p10 = base + (r1 + x0) * rowb;
+  r.p11 = base + (r1 + x1) * rowb;
+  return r;
 }
 
 template <int MODE, typename VT, int LANES, int NV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (LANES == 32) ? 2 : 4)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (LANES == 32) ? 2 : 3)
 xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap) {
   constexpr int VEC = Slice<VT>::VEC;
   constexpr int PL = VEC * NV;
   constexpr int GROUPS = 32 / LANES;  // items per warp-wide load
   constexpr bool WIDE = (LANES == 32);
+  constexpr int INF = 4 / NV;         // items in flight per group: 16 gathers per lane
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  const int lane_ = threadIdx.x & 31;
-  const int grp = lane_ / LANES;
-  const int sub = lane_ % LANES;
-  const size_t warp_bytes = sizeof(float) * kMaxLP + sizeof(Cand) * cand_cap;
-  float* sw = reinterpret_cast<float*>(smem_raw + warp * warp_bytes);
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / LANES;
+  const int sub = lane % LANES;
+  const size_t warp_bytes = sizeof(RecF) * 32 + sizeof(float) * kMaxLP + sizeof(Cand) * cand_cap;
+  RecF* recs = reinterpret_cast<RecF*>(smem_raw + warp * warp_bytes);
+  float* sw = reinterpret_cast<float*>(recs + 32);
   Cand* cands = reinterpret_cast<Cand*>(sw + kMaxLP);
+  const int lane_off = sub * 16;      // this lane's 16 bytes inside a (LANES*16)-byte run
 
   WorkIter wi;
   work_begin(p, wi);
@@ -139,16 +125,53 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     float acc[PL];
 #pragma unroll
     for (int i = 0; i < PL; ++i) acc[i] = 0.f;
-    float wsum = 0.f;
+    float wsum_lane = 0.f;
     const int total = nvalid * p.L;
-    for (int it0 = 0; it0 < total; it0 += 2 * GROUPS) {
-      ItemLoad<VT, NV> la, lb;
-      item_issue<MODE, VT, LANES, NV>(p, cands, sw, it0 + grp, total, w, sub, la);
-      item_issue<MODE, VT, LANES, NV>(p, cands, sw, it0 + GROUPS + grp, total, w, sub, lb);
-      item_pin<VT, NV>(la);
-      item_pin<VT, NV>(lb);
-      item_consume<VT, NV>(la, acc, wsum);
-      item_consume<VT, NV>(lb, acc, wsum);
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      recs[lane] = build_record<MODE, VT, WIDE>(p, cands, sw, c0 + lane, total, w, wsum_lane);
+      __syncwarp();
+      const int nchunk = min(32, total - c0);
+      for (int j0 = 0; j0 < nchunk; j0 += INF * GROUPS) {
+        uint4 raw[INF][4][NV];
+        float wgt[INF][4];
+#pragma unroll
+        for (int u = 0; u < INF; ++u) {
+          const RecF r = recs[j0 + u * GROUPS + grp];
+          wgt[u][0] = r.w00; wgt[u][1] = r.w01; wgt[u][2] = r.w10; wgt[u][3] = r.w11;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const int o = lane_off + j * LANES * 16;
+            raw[u][0][j] = ldg_nc_v4_all(r.p00 + o);
+            raw[u][1][j] = ldg_nc_v4_all(r.p01 + o);
+            raw[u][2][j] = ldg_nc_v4_all(r.p10 + o);
+            raw[u][3][j] = ldg_nc_v4_all(r.p11 + o);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < INF; ++u)
+#pragma unroll
+          for (int j = 0; j < NV; ++j) pin(raw[u][0][j], raw[u][1][j], raw[u][2][j], raw[u][3][j]);
+#pragma unroll
+        for (int u = 0; u < INF; ++u)
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            float c00[VEC], c01[VEC], c10[VEC], c11[VEC];
+            Slice<VT>::unpack(raw[u][0][j], c00);
+            Slice<VT>::unpack(raw[u][1][j], c01);
+            Slice<VT>::unpack(raw[u][2][j], c10);
+            Slice<VT>::unpack(raw[u][3][j], c11);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              float a = acc[j * VEC + i];
+              a = fmaf(wgt[u][0], c00[i], a);
+              a = fmaf(wgt[u][1], c01[i], a);
+              a = fmaf(wgt[u][2], c10[i], a);
+              a = fmaf(wgt[u][3], c11[i], a);
+              acc[j * VEC + i] = a;
+            }
+          }
+      }
+      __syncwarp();  // records are rebuilt by the next chunk
     }
 
     // ---- reduce across lane groups, store ----------------------------------------------
@@ -167,7 +190,11 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
           *reinterpret_cast<float4*>(o + (j * LANES + sub) * VEC + i) = make_float4(
               acc[j * VEC + i], acc[j * VEC + i + 1], acc[j * VEC + i + 2], acc[j * VEC + i + 3]);
     }
-    if (WIDE && p.wsum != nullptr && w.lane == 0) p.wsum[static_cast<size_t>(w.bq) * p.Hh + w.h] = wsum;
+    if (WIDE && p.wsum != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wsum_lane += __shfl_xor_sync(0xffffffffu, wsum_lane, o);
+      if (lane == 0) p.wsum[static_cast<size_t>(w.bq) * p.Hh + w.h] = wsum_lane;
+    }
     __syncwarp();  // the per-warp shared-memory lists are reused by the next work item
   }
   work_end(p, wi);
