@@ -63,7 +63,8 @@ static int validate(const gd4d_xview_params* p, bool backward, LaunchGeom* g) {
   const bool big = backward || p->mode == GD4D_MODE_V2;   // V2 uses the backward layout both ways
   const long long per_cand = big ? 32 : 16;
   // forward: 32 gather records of 48 B + softmax weights + candidates
-  const long long per_warp = big ? sizeof(float) * kMaxLP * 5 + per_cand * cand_cap
+  const long long recb = (backward && p->mode != GD4D_MODE_V2) ? 32 * 96 : 0;  // backward records
+  const long long per_warp = big ? recb + sizeof(float) * kMaxLP * 5 + per_cand * cand_cap
                                  : 32 * 48 + sizeof(float) * kMaxLP + per_cand * cand_cap;
   const long long smem = per_warp * kWarpsPerCta;
   if (smem > 200 * 1024) return GD4D_ERR_UNSUPPORTED;

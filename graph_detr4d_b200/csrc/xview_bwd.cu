@@ -41,23 +41,88 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+// Backward record of one (candidate, level) item, built by ONE lane (see xview_fwd.cu).
+// Corner offsets are clamped into the map (always valid addresses); every coefficient
+// already carries the in-bounds mask, so out-of-map corners contribute exact zeros:
+//   s      = sum_c w_c  f_c          (bilinear sample)
+//   W*ds/dix = sum_c ax_c f_c ,  H*ds/diy = sum_c ay_c f_c
+struct __align__(16) RecB {
+  long long o00, o01, o10, o11;   // element offsets of the 4 corner rows (without lane offset)
+  float w00, w01, w10, w11;
+  float ax00, ax01, ax10, ax11;
+  float ay00, ay01, ay10, ay11;
+  float wt, smw, cw;              // total weight, softmax weight, camera weight
+  int meta;                       // active<<31 | k<<16 | slot<<8 | l
+};
+
+template <int MODE, typename VT, bool WIDE>
+__device__ __forceinline__ RecB build_record_bwd(const gd4d_xview_params& p, const CandB* cands,
+                                                 const float* sw, int item, int total,
+                                                 const WarpCtx& w) {
+  RecB r;
+  const bool active = item < total;
+  const int it = active ? item : 0;
+  const int k = it / p.L;
+  const int l = it - k * p.L;
+  const int np = cands[k].np;
+  const float cu = cands[k].u, cv = cands[k].v, cw = cands[k].w;
+  const int n = np >> 8;
+  const int pi = np & 0xff;
+  float wt, smw = 0.f;
+  if (MODE == GD4D_MODE_C) {
+    smw = sw[l * p.P + pi];
+    wt = smw * cw;
+  } else {
+    const float* a = p.attn_logits + (static_cast<size_t>(w.bq) * p.N + n) * p.P * p.L + l;
+    wt = 0.f;
+    for (int pp = 0; pp < p.P; ++pp) wt += sigmoidf_(__ldg(a + pp * p.L));
+  }
+  if (!active) wt = 0.f;
+  const int W = p.level_w[l], H = p.level_h[l];
+  const float ix = to_pixel(to_grid<MODE>(cu), static_cast<float>(W));
+  const float iy = to_pixel(to_grid<MODE>(cv), static_cast<float>(H));
+  const Footprint f = footprint(ix, iy, W, H);
+  const float m00 = f.in00 ? 1.f : 0.f, m01 = f.in01 ? 1.f : 0.f;
+  const float m10 = f.in10 ? 1.f : 0.f, m11 = f.in11 ? 1.f : 0.f;
+  const float fW = static_cast<float>(W), fH = static_cast<float>(H);
+  r.w00 = m00 * (1.f - f.tx) * (1.f - f.ty); r.w01 = m01 * f.tx * (1.f - f.ty);
+  r.w10 = m10 * (1.f - f.tx) * f.ty;         r.w11 = m11 * f.tx * f.ty;
+  r.ax00 = -m00 * (1.f - f.ty) * fW; r.ax01 = m01 * (1.f - f.ty) * fW;
+  r.ax10 = -m10 * f.ty * fW;         r.ax11 = m11 * f.ty * fW;
+  r.ay00 = -m00 * (1.f - f.tx) * fH; r.ay10 = m10 * (1.f - f.tx) * fH;
+  r.ay01 = -m01 * f.tx * fH;         r.ay11 = m11 * f.tx * fH;
+  r.wt = wt; r.smw = smw; r.cw = cw;
+  r.meta = (active ? (1 << 31) : 0) | (k << 16) | ((l * p.P + pi) << 8) | l;
+  const int x0 = min(max(f.x0, 0), W - 1), x1 = min(max(f.x0 + 1, 0), W - 1);
+  const int y0 = min(max(f.y0, 0), H - 1), y1 = min(max(f.y0 + 1, 0), H - 1);
+  const long long img = static_cast<long long>(w.b) * p.N + n;
+  const long long base = img * H * W * p.C + (WIDE ? 0 : w.h * kHeadDim);
+  r.o00 = base + (static_cast<long long>(y0) * W + x0) * p.C;
+  r.o01 = base + (static_cast<long long>(y0) * W + x1) * p.C;
+  r.o10 = base + (static_cast<long long>(y1) * W + x0) * p.C;
+  r.o11 = base + (static_cast<long long>(y1) * W + x1) * p.C;
+  return r;
+}
+
 template <int MODE, typename VT, int LANES, int NV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (LANES == 32) ? 2 : 3)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap) {
   constexpr int VEC = Slice<VT>::VEC;
   constexpr int PL = VEC * NV;
   constexpr int GROUPS = 32 / LANES;
   constexpr bool WIDE = (LANES == 32);
+  constexpr int INF = 2;  // items in flight per group
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int grp = lane / LANES;
   const int sub = lane % LANES;
-  const size_t warp_bytes = sizeof(float) * kMaxLP * 5 + sizeof(CandB) * cand_cap;
-  float* sw = reinterpret_cast<float*>(smem_raw + warp * warp_bytes);  // softmax weights
-  float* gsum = sw + kMaxLP;                                           // sum_n wcam*(s.g) per (l,p)
-  float* doff = gsum + kMaxLP;                                         // dL/d offset (p,3)
+  const size_t warp_bytes = sizeof(RecB) * 32 + sizeof(float) * kMaxLP * 5 + sizeof(CandB) * cand_cap;
+  RecB* recs = reinterpret_cast<RecB*>(smem_raw + warp * warp_bytes);
+  float* sw = reinterpret_cast<float*>(recs + 32);  // softmax weights
+  float* gsum = sw + kMaxLP;                        // sum_n wcam*(s.g) per (l,p)
+  float* doff = gsum + kMaxLP;                      // dL/d offset (p,3)
   CandB* cands = reinterpret_cast<CandB*>(doff + 3 * kMaxLP);
   const int LP = p.L * p.P;
 
@@ -70,13 +135,33 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     {
       const float* go = WIDE ? p.grad_out + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.C
                              : p.grad_out + static_cast<size_t>(w.bq) * p.C + w.h * kHeadDim;
-  #pragma unroll
+#pragma unroll
       for (int j = 0; j < NV; ++j)
-  #pragma unroll
+#pragma unroll
         for (int i = 0; i < VEC; i += 4) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(go + (j * LANES + sub) * VEC + i));
           g[j * VEC + i] = t.x; g[j * VEC + i + 1] = t.y; g[j * VEC + i + 2] = t.z; g[j * VEC + i + 3] = t.w;
         }
+    }
+    // The feature-gradient reductions use their own channel->lane map: vector r of a lane
+    // sits at channel (r*LANES + sub)*4, so that every warp-wide RED instruction covers
+    // LANES*16 CONTIGUOUS bytes of the fp32 grad row.  For fp32 maps that equals the load
+    // layout; for bf16 maps (8 channels per 16-byte load) it does not, and reusing the
+    // load layout would make each RED touch 16 of every 32 bytes (r1: 2x slower atomics).
+    constexpr int NR = PL / 4;
+    float gr[NR][4];
+    {
+      const float* go = WIDE ? p.grad_out + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.C
+                             : p.grad_out + static_cast<size_t>(w.bq) * p.C + w.h * kHeadDim;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if (VEC == 4) {
+          gr[r][0] = g[r * 4]; gr[r][1] = g[r * 4 + 1]; gr[r][2] = g[r * 4 + 2]; gr[r][3] = g[r * 4 + 3];
+        } else {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(go + (r * LANES + sub) * 4));
+          gr[r][0] = t.x; gr[r][1] = t.y; gr[r][2] = t.z; gr[r][3] = t.w;
+        }
+      }
     }
     const float gws = (WIDE && p.grad_wsum != nullptr)
                           ? __ldg(p.grad_wsum + static_cast<size_t>(w.bq) * p.Hh + w.h) : 0.f;
@@ -89,115 +174,110 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     }
     const int nvalid = build_candidates<MODE, CandB>(p, w, cands, false);
 
-    // ---- phase 2: re-gather, dot with grad_out, scatter feature gradients ---------------------
+    // ---- phase 2: re-gather, dot with grad_out, scatter feature gradients -------------------
     const int total = nvalid * p.L;
-    for (int it0 = 0; it0 < total; it0 += GROUPS) {
-      const int item = it0 + grp;
-      const bool active = item < total;
-      const int it = active ? item : 0;
-      const int k = it / p.L;
-      const int l = it - k * p.L;
-      const int np = cands[k].np;
-      const float cu = cands[k].u, cv = cands[k].v, cw = cands[k].w;
-      const int n = np >> 8;
-      const int pi = np & 0xff;
-      float wt, smw = 0.f;
-      const float* alog = nullptr;
-      if (MODE == GD4D_MODE_C) {
-        smw = sw[l * p.P + pi];
-        wt = smw * cw;
-      } else {
-        alog = p.attn_logits + (static_cast<size_t>(w.bq) * p.N + n) * p.P * p.L + l;
-        wt = 0.f;
-        for (int pp = 0; pp < p.P; ++pp) wt += sigmoidf_(__ldg(alog + pp * p.L));
-      }
-      if (!active) wt = 0.f;
-      const int W = p.level_w[l], H = p.level_h[l];
-      const float ix = to_pixel(to_grid<MODE>(cu), static_cast<float>(W));
-      const float iy = to_pixel(to_grid<MODE>(cv), static_cast<float>(H));
-      const Footprint f = footprint(ix, iy, W, H);
-      const VT* base = static_cast<const VT*>(p.value[l]);
-      const size_t img = static_cast<size_t>(w.b) * p.N + n;
-      const size_t e00 = ((img * H + f.y0) * W + f.x0) * p.C +
-                         (WIDE ? 0 : static_cast<size_t>(w.h) * kHeadDim) + sub * VEC;
-      const size_t rowst = static_cast<size_t>(W) * p.C;
-      float c00[PL], c01[PL], c10[PL], c11[PL];
-      const bool a00 = active & f.in00, a01 = active & f.in01, a10 = active & f.in10, a11 = active & f.in11;
-      {
-        uint4 r00[NV], r01[NV], r10[NV], r11[NV];
-  #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int o = j * LANES * VEC;
-          r00[j] = ldg_nc_v4(base + e00 + o, a00);
-          r01[j] = ldg_nc_v4(base + e00 + p.C + o, a01);
-          r10[j] = ldg_nc_v4(base + e00 + rowst + o, a10);
-          r11[j] = ldg_nc_v4(base + e00 + rowst + p.C + o, a11);
-        }
-  #pragma unroll
-        for (int j = 0; j < NV; ++j) pin(r00[j], r01[j], r10[j], r11[j]);
-  #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          Slice<VT>::unpack(r00[j], &c00[j * VEC]);
-          Slice<VT>::unpack(r01[j], &c01[j * VEC]);
-          Slice<VT>::unpack(r10[j], &c10[j * VEC]);
-          Slice<VT>::unpack(r11[j], &c11[j * VEC]);
-        }
-      }
-      const float w00 = (1.f - f.tx) * (1.f - f.ty), w01 = f.tx * (1.f - f.ty);
-      const float w10 = (1.f - f.tx) * f.ty, w11 = f.tx * f.ty;
-
-      // feature-map gradient: dL/df_c += wt * w_c * g   (vector reductions, no return value)
-      float* gv = p.grad_value[l];
-      if (gv != nullptr && wt != 0.f) {
-        const float s00 = wt * w00, s01 = wt * w01, s10 = wt * w10, s11 = wt * w11;
-  #pragma unroll
-        for (int j = 0; j < NV; ++j)
-  #pragma unroll
-          for (int i = 0; i < VEC; i += 4) {
-            const int o = j * LANES * VEC + i;
-            const float g0 = g[j * VEC + i], g1 = g[j * VEC + i + 1], g2 = g[j * VEC + i + 2],
-                        g3 = g[j * VEC + i + 3];
-            if (a00) red_add_v4(gv + e00 + o, s00 * g0, s00 * g1, s00 * g2, s00 * g3);
-            if (a01) red_add_v4(gv + e00 + p.C + o, s01 * g0, s01 * g1, s01 * g2, s01 * g3);
-            if (a10) red_add_v4(gv + e00 + rowst + o, s10 * g0, s10 * g1, s10 * g2, s10 * g3);
-            if (a11) red_add_v4(gv + e00 + rowst + p.C + o, s11 * g0, s11 * g1, s11 * g2, s11 * g3);
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      recs[lane] = build_record_bwd<MODE, VT, WIDE>(p, cands, sw, c0 + lane, total, w);
+      __syncwarp();
+      const int nchunk = min(32, total - c0);
+      for (int j0 = 0; j0 < nchunk; j0 += INF * GROUPS) {
+        uint4 raw[INF][4][NV];
+#pragma unroll
+        for (int u = 0; u < INF; ++u) {
+          const RecB* r = recs + (j0 + u * GROUPS + grp);
+          const VT* base = static_cast<const VT*>(p.value[r->meta & 0xff]) + sub * VEC;
+          const long long o00 = r->o00, o01 = r->o01, o10 = r->o10, o11 = r->o11;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const int o = j * LANES * VEC;
+            raw[u][0][j] = ldg_nc_v4_all(reinterpret_cast<const char*>(base + o00 + o));
+            raw[u][1][j] = ldg_nc_v4_all(reinterpret_cast<const char*>(base + o01 + o));
+            raw[u][2][j] = ldg_nc_v4_all(reinterpret_cast<const char*>(base + o10 + o));
+            raw[u][3][j] = ldg_nc_v4_all(reinterpret_cast<const char*>(base + o11 + o));
           }
-      }
+        }
+#pragma unroll
+        for (int u = 0; u < INF; ++u)
+#pragma unroll
+          for (int j = 0; j < NV; ++j) pin(raw[u][0][j], raw[u][1][j], raw[u][2][j], raw[u][3][j]);
 
-      float sdot = 0.f, dxdot = 0.f, dydot = 0.f;
-  #pragma unroll
-      for (int i = 0; i < PL; ++i) {
-        sdot += g[i] * (w00 * c00[i] + w01 * c01[i] + w10 * c10[i] + w11 * c11[i]);
-        dxdot += g[i] * ((c01[i] - c00[i]) * (1.f - f.ty) + (c11[i] - c10[i]) * f.ty);
-        dydot += g[i] * ((c10[i] - c00[i]) * (1.f - f.tx) + (c11[i] - c01[i]) * f.tx);
-      }
-  #pragma unroll
-      for (int o = 1; o < LANES; o <<= 1) {
-        sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
-        dxdot += __shfl_xor_sync(0xffffffffu, dxdot, o);
-        dydot += __shfl_xor_sync(0xffffffffu, dydot, o);
-      }
-      if (WIDE) {  // the bias rides as an all-ones channel: 1 inside the map, 0 outside
-        const float i00 = f.in00 ? 1.f : 0.f, i01 = f.in01 ? 1.f : 0.f, i10 = f.in10 ? 1.f : 0.f,
-                    i11 = f.in11 ? 1.f : 0.f;
-        sdot += gws * (w00 * i00 + w01 * i01 + w10 * i10 + w11 * i11);
-        dxdot += gws * ((i01 - i00) * (1.f - f.ty) + (i11 - i10) * f.ty);
-        dydot += gws * ((i10 - i00) * (1.f - f.tx) + (i11 - i01) * f.tx);
-      }
-      if (active && sub == 0) {
-        atomicAdd(&cands[k].du, wt * static_cast<float>(W) * dxdot);
-        atomicAdd(&cands[k].dv, wt * static_cast<float>(H) * dydot);
-        if (MODE == GD4D_MODE_C) {
-          atomicAdd(&gsum[l * p.P + pi], cw * sdot);
-          atomicAdd(&cands[k].cg, smw * sdot);
-        } else if (p.grad_attn_logits != nullptr) {
-          float* ga = p.grad_attn_logits + (alog - p.attn_logits);
-          for (int pp = 0; pp < p.P; ++pp) {
-            const float sg = sigmoidf_(__ldg(alog + pp * p.L));
-            atomicAdd(ga + pp * p.L, sg * (1.f - sg) * sdot);
+#pragma unroll
+        for (int u = 0; u < INF; ++u) {
+          const RecB* r = recs + (j0 + u * GROUPS + grp);
+          const int meta = r->meta;
+          const bool active = meta < 0;
+          const int l = meta & 0xff;
+          const float wt = r->wt;
+          const float w00 = r->w00, w01 = r->w01, w10 = r->w10, w11 = r->w11;
+
+          // feature-map gradient: dL/df_c += wt * w_c * g   (vector reductions, no return value)
+          float* gv = p.grad_value[l];
+          if (gv != nullptr && wt != 0.f) {
+            gv += sub * 4;
+            const float s00 = wt * w00, s01 = wt * w01, s10 = wt * w10, s11 = wt * w11;
+            const long long o00 = r->o00, o01 = r->o01, o10 = r->o10, o11 = r->o11;
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+              const int o = q * LANES * 4;
+              const float g0 = gr[q][0], g1 = gr[q][1], g2 = gr[q][2], g3 = gr[q][3];
+              if (s00 != 0.f) red_add_v4(gv + o00 + o, s00 * g0, s00 * g1, s00 * g2, s00 * g3);
+              if (s01 != 0.f) red_add_v4(gv + o01 + o, s01 * g0, s01 * g1, s01 * g2, s01 * g3);
+              if (s10 != 0.f) red_add_v4(gv + o10 + o, s10 * g0, s10 * g1, s10 * g2, s10 * g3);
+              if (s11 != 0.f) red_add_v4(gv + o11 + o, s11 * g0, s11 * g1, s11 * g2, s11 * g3);
+            }
+          }
+
+          // per-corner dot products with grad_out, then three scalar combinations
+          float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            float c00[VEC], c01[VEC], c10[VEC], c11[VEC];
+            Slice<VT>::unpack(raw[u][0][j], c00);
+            Slice<VT>::unpack(raw[u][1][j], c01);
+            Slice<VT>::unpack(raw[u][2][j], c10);
+            Slice<VT>::unpack(raw[u][3][j], c11);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              const float gi = g[j * VEC + i];
+              d00 = fmaf(gi, c00[i], d00);
+              d01 = fmaf(gi, c01[i], d01);
+              d10 = fmaf(gi, c10[i], d10);
+              d11 = fmaf(gi, c11[i], d11);
+            }
+          }
+          float sdot = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;
+          float dxdot = r->ax00 * d00 + r->ax01 * d01 + r->ax10 * d10 + r->ax11 * d11;  // W * ds/dix . g
+          float dydot = r->ay00 * d00 + r->ay01 * d01 + r->ay10 * d10 + r->ay11 * d11;  // H * ds/diy . g
+#pragma unroll
+          for (int o = 1; o < LANES; o <<= 1) {
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+            dxdot += __shfl_xor_sync(0xffffffffu, dxdot, o);
+            dydot += __shfl_xor_sync(0xffffffffu, dydot, o);
+          }
+          if (WIDE) {  // the bias rides as an all-ones channel: 1 inside the map, 0 outside
+            sdot += gws * (w00 + w01 + w10 + w11);
+            dxdot += gws * (r->ax00 + r->ax01 + r->ax10 + r->ax11);
+            dydot += gws * (r->ay00 + r->ay01 + r->ay10 + r->ay11);
+          }
+          if (active && sub == 0) {
+            const int k = (meta >> 16) & 0x7fff;
+            atomicAdd(&cands[k].du, wt * dxdot);
+            atomicAdd(&cands[k].dv, wt * dydot);
+            if (MODE == GD4D_MODE_C) {
+              atomicAdd(&gsum[(meta >> 8) & 0xff], r->cw * sdot);
+              atomicAdd(&cands[k].cg, r->smw * sdot);
+            } else if (p.grad_attn_logits != nullptr) {
+              const int n = cands[k].np >> 8;
+              const size_t ao = (static_cast<size_t>(w.bq) * p.N + n) * p.P * p.L + l;
+              for (int pp = 0; pp < p.P; ++pp) {
+                const float sg = sigmoidf_(__ldg(p.attn_logits + ao + pp * p.L));
+                atomicAdd(p.grad_attn_logits + ao + pp * p.L, sg * (1.f - sg) * sdot);
+              }
+            }
           }
         }
       }
+      __syncwarp();  // records are rebuilt by the next chunk
     }
     __syncwarp();
 
@@ -207,7 +287,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
       const float s0 = sw[lane], s1 = sw[lane + 32];
       const float g0 = gsum[lane], g1 = gsum[lane + 32];
       float dot = s0 * g0 + s1 * g1;
-  #pragma unroll
+#pragma unroll
       for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
       float* ga = p.grad_attn_logits + (static_cast<size_t>(w.bq) * p.Hh + w.h) * LP;
       if (lane < LP) atomicAdd(ga + lane, s0 * (g0 - dot));
@@ -238,7 +318,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
       }
     }
     if (p.grad_ref != nullptr) {
-  #pragma unroll
+#pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         rX += __shfl_xor_sync(0xffffffffu, rX, o);
         rY += __shfl_xor_sync(0xffffffffu, rY, o);
