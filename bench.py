@@ -314,7 +314,10 @@ def main():
                     ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype=dtype, data="synthetic",
                     config=dict(workload=workload_name(T, dtype), layers=LAYERS, queries=Q, cams=N,
-                                points=POINTS, heads=HEADS, per_gpu_batch=1, optimizer="AdamW(fused)",
+                                points=POINTS, heads=HEADS, per_gpu_batch=1, optimizer="AdamW(fused, capturable)",
+                                value_proj="fused: gather-then-project (no dense per-pixel GEMM)",
+                                execution="CUDA graphs (fwd+bwd graph, NCCL all-reduce of flat grads if N>1, optimizer graph)",
+                                features="NCHW fp32 in, packed channel-last once per step inside the step",
                                 parallelism=f"dp{world}" if world > 1 else "single",
                                 l2="inputs larger than L2 (feature maps + dense grad maps >= 2x126 MB per layer)"),
                     e2e=dict(value=e2e_val, unit=UNIT, ms_per_step=ms_e2e / K,
