@@ -13,10 +13,11 @@ import threading
 
 from . import _build
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LEVELS = 8
 MODE_A, MODE_C, MODE_V2 = 0, 1, 2
 F32, BF16 = 0, 1
+FLAG_TMA_FORWARD = 1
 
 EXPORTS = (
     "gd4d_abi_version",
@@ -38,6 +39,7 @@ class XViewParams(C.Structure):
         ("B", C.c_int32), ("Q", C.c_int32), ("N", C.c_int32), ("Hh", C.c_int32),
         ("L", C.c_int32), ("P", C.c_int32), ("C", C.c_int32),
         ("wide", C.c_int32),
+        ("flags", C.c_uint32),
         ("level_h", C.c_int32 * MAX_LEVELS),
         ("level_w", C.c_int32 * MAX_LEVELS),
         ("pc_lo", C.c_float * 3),

@@ -5,6 +5,7 @@
 namespace gd4d {
 int dispatch_forward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
 int dispatch_backward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
+int dispatch_forward_tma(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
 int dispatch_v2(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream, bool backward);
 int dispatch_pack(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t images, int C,
                   int H, int W, cudaStream_t stream);
@@ -112,6 +113,8 @@ int gd4d_xview_forward(const gd4d_xview_params* p, void* cuda_stream) {
   if (st != GD4D_OK) return st;
   if (p->mode == GD4D_MODE_V2)
     return gd4d::dispatch_v2(*p, g, static_cast<cudaStream_t>(cuda_stream), false);
+  if (p->mode == GD4D_MODE_C && p->wide && p->sched != nullptr && (p->flags & GD4D_FLAG_TMA_FORWARD))
+    return gd4d::dispatch_forward_tma(*p, g, static_cast<cudaStream_t>(cuda_stream));
   return gd4d::dispatch_forward(*p, g, static_cast<cudaStream_t>(cuda_stream));
 }
 

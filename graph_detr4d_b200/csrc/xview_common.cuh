@@ -208,10 +208,11 @@ __device__ __forceinline__ bool work_next(const gd4d_xview_params& p, WorkIter& 
   return true;
 }
 
-__device__ __forceinline__ void work_end(const gd4d_xview_params& p, const WorkIter& it) {
+__device__ __forceinline__ void work_end(const gd4d_xview_params& p, const WorkIter& it,
+                                         int warps_per_cta = kWarpsPerCta) {
   if (!it.dynamic) return;
   if ((threadIdx.x & 31) == 0) {
-    const unsigned warps = gridDim.x * kWarpsPerCta;
+    const unsigned warps = gridDim.x * warps_per_cta;
     const unsigned done = atomicAdd(p.sched + 1, 1u);
     if (done == warps - 1) {  // every warp has made its final (failing) claim: safe to reset
       p.sched[0] = 0u;

@@ -21,6 +21,7 @@ __all__ = ["XViewConfig", "pack_features", "PackedFeatures", "xview_forward", "x
            "launch_count", "MODE_A", "MODE_C", "MODE_V2"]
 
 DYNAMIC_SCHEDULE = True   # persistent grid + work counter (False: one warp per item, static)
+TMA_FORWARD = False       # wide forward through the cp.async.bulk staging path (xview_fwd_tma.cu)
 _LAUNCHES = 0      # kernels of libgd4d_xview.so launched by this process (bench: gpu_launches)
 
 
@@ -267,6 +268,8 @@ def _fill_params(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: in
     if DYNAMIC_SCHEDULE and cfg.mode == MODE_C:
         # mode A launches are ~10 us of work: the per-item claim costs more than the tail it removes
         p.sched = _sched_ptr(ref.device)
+        if TMA_FORWARD and cfg.wide:
+            p.flags = _lib.FLAG_TMA_FORWARD
     return p
 
 

@@ -40,7 +40,7 @@ extern "C" {
 #define GD4D_API
 #endif
 
-#define GD4D_ABI_VERSION 3
+#define GD4D_ABI_VERSION 4
 #define GD4D_MAX_LEVELS 8
 
 typedef enum gd4d_status {
@@ -60,6 +60,10 @@ typedef enum gd4d_mode {
 } gd4d_mode;
 
 typedef enum gd4d_dtype { GD4D_F32 = 0, GD4D_BF16 = 1 } gd4d_dtype;
+
+/* forward, wide mode, sched set: stage the corner rows in shared memory with TMA bulk
+ * copies (cp.async.bulk + mbarrier pipeline) instead of register gathers */
+#define GD4D_FLAG_TMA_FORWARD 1u
 
 /*
  * One decoder-layer invocation.  All pointers are device pointers.
@@ -107,6 +111,7 @@ typedef struct gd4d_xview_params {
   int32_t value_dtype;          /* gd4d_dtype */
   int32_t B, Q, N, Hh, L, P, C;
   int32_t wide;                 /* mode C only: 0 = head slices of projected value, 1 = see above */
+  uint32_t flags;               /* GD4D_FLAG_* */
   int32_t level_h[GD4D_MAX_LEVELS];
   int32_t level_w[GD4D_MAX_LEVELS];
   float pc_lo[3];               /* pc_range[0:3]                              */

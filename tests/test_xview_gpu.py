@@ -299,3 +299,27 @@ def test_mode_v2_forward_backward(T, Q, dtype):
     assert H.rel_err(ref_g.grad.cpu(), ref_o.grad) <= GRAD_TOL
     for fg, fo in zip(feats_g, feats_o):
         assert H.rel_err(fg.grad.cpu(), fo.grad) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("C,dtype,T,Q", [(256, torch.float32, 2, 333), (256, torch.bfloat16, 2, 200),
+                                         (128, torch.float32, 1, 64)])
+def test_tma_forward_path_matches_register_gather_path(C, dtype, T, Q):
+    """cp.async.bulk + mbarrier staging (xview_fwd_tma.cu) vs the LDG kernel and the oracle."""
+    sc = H.scene(B=1, T=T, Q=Q, C=C)
+    logits, offsets, cam = H.rand_inputs_c(sc)
+    feats_src = [f.to(dtype).float() for f in sc["feats"]]
+    packed = _pack(feats_src, dtype)
+    cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=True)
+    args = (cfg, packed.levels, 1, sc["N"], sc["ref"].cuda(), logits.cuda(), offsets.cuda(), cam.cuda(),
+            sc["l2i"].cuda())
+    (o_ldg, ws_ldg), _ = ops.xview_forward(*args)
+    ops.TMA_FORWARD = True
+    try:
+        for _ in range(3):                              # mbarrier phases must survive relaunches
+            (o_tma, ws_tma), m = ops.xview_forward(*args, want_mask=True)
+    finally:
+        ops.TMA_FORWARD = False
+    agg_o, ws_o = xo.xview_c_wide_core(feats_src, sc["ref"], offsets, logits, cam, sc["l2i"], syn.PC_RANGE,
+                                       900, 1600, 8)
+    assert H.rel_err(o_tma.cpu(), agg_o) <= FWD_TOL and H.rel_err(ws_tma.cpu(), ws_o) <= FWD_TOL
+    assert H.rel_err(o_tma, o_ldg) <= 1e-6 and H.rel_err(ws_tma, ws_ldg) <= 1e-6

@@ -41,6 +41,7 @@ for name, mode, T, dtype in [("C_T1_fp32", MODE_C, 1, torch.float32), ("C_T2_fp3
     gout = torch.randn_like(out)
     gvals = [torch.zeros(v.shape, device='cuda', dtype=torch.float32) for v in packed.levels]
     if "--static" in _s.argv: ops.DYNAMIC_SCHEDULE = False
+    if "--tma" in _s.argv: ops.TMA_FORWARD = True
     fprep = ops.prepare_forward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i)
     fwd = fprep.launch
     bprep = ops.prepare_backward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i, gout, gvals)
