@@ -323,3 +323,13 @@ def test_tma_forward_path_matches_register_gather_path(C, dtype, T, Q):
                                        900, 1600, 8)
     assert H.rel_err(o_tma.cpu(), agg_o) <= FWD_TOL and H.rel_err(ws_tma.cpu(), ws_o) <= FWD_TOL
     assert H.rel_err(o_tma, o_ldg) <= 1e-6 and H.rel_err(ws_tma, ws_ldg) <= 1e-6
+
+
+@pytest.mark.parametrize("C,H_,W_", [(256, 12, 20), (36, 8, 13), (64, 29, 50), (256, 15, 25), (40, 4, 33)])
+def test_pack_kernels_exact_all_paths(C, H_, W_):
+    """Vectorised swizzled path (HW % 4 == 0) and the scalar fallback, tile tails included."""
+    g = torch.Generator().manual_seed(C + H_)
+    f = torch.randn(2, 3, C, H_, W_, generator=g).cuda()
+    want = f.flatten(0, 1).permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(ops.pack_level(f), want)
+    assert torch.equal(ops.pack_level(f, torch.bfloat16), want.to(torch.bfloat16))
