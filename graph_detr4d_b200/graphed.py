@@ -11,7 +11,9 @@ Data-parallel use (one process per GPU): gradients live in ONE flat fp32 buffer
 (every ``param.grad`` is a view of it), so the only collective of the step is a
 single NCCL all-reduce of that buffer between the captured forward/backward and
 the captured optimizer step (the sampling path itself needs no
-communication).
+communication).  (r1: capturing the NCCL all-reduce INSIDE the step graph was tried and
+hung during capture with torch 2.11 / NCCL 2.28 on 2 GPUs; the collective therefore stays an
+eager, stream-ordered call between the two graphs.)
 """
 from __future__ import annotations
 
