@@ -92,7 +92,9 @@ __device__ __forceinline__ RecB build_record_bwd(const gd4d_xview_params& p, con
   r.ay00 = -m00 * (1.f - f.tx) * fH; r.ay10 = m10 * (1.f - f.tx) * fH;
   r.ay01 = -m01 * f.tx * fH;         r.ay11 = m11 * f.tx * fH;
   r.wt = wt; r.smw = smw; r.cw = cw;
-  r.meta = (active ? (1 << 31) : 0) | (k << 16) | ((l * p.P + pi) << 8) | l;
+  const int slot = (MODE == GD4D_MODE_C) ? (l * p.P + pi) : 0;  // softmax slot (<= 63); unused in mode A
+  r.meta = static_cast<int>((active ? 0x80000000u : 0u) | (static_cast<unsigned>(k) << 16) |
+                            (static_cast<unsigned>(slot) << 8) | static_cast<unsigned>(l));
   const int x0 = min(max(f.x0, 0), W - 1), x1 = min(max(f.x0 + 1, 0), W - 1);
   const int y0 = min(max(f.y0, 0), H - 1), y1 = min(max(f.y0 + 1, 0), H - 1);
   const long long img = static_cast<long long>(w.b) * p.N + n;

@@ -247,7 +247,7 @@ def _position_encoder(in_dims, embed_dims):
 # ----------------------------------------------------------------------------------------
 # variant A
 # ----------------------------------------------------------------------------------------
-@ATTENTION.register_module()
+@ATTENTION.register_module(force=True)
 class Detr3DCrossAtten(BaseModule):
     """DETR3D centre-point cross-view attention (detr3d_transformer.py:229-390)."""
 
@@ -311,7 +311,7 @@ class Detr3DCrossAtten(BaseModule):
 # ----------------------------------------------------------------------------------------
 # variant V2 (registered by the reference, used by no config)
 # ----------------------------------------------------------------------------------------
-@ATTENTION.register_module()
+@ATTENTION.register_module(force=True)
 class Detr3DCrossAttenV2(BaseModule):
     """Deformable-DETR style 2D offsets around the projected centre
     (detr3d_transformer.py:441-709).  Like the reference it needs
@@ -387,7 +387,7 @@ class Detr3DCrossAttenV2(BaseModule):
 # ----------------------------------------------------------------------------------------
 # variant C (Graph-DETR4D)
 # ----------------------------------------------------------------------------------------
-@ATTENTION.register_module()
+@ATTENTION.register_module(force=True)
 class Deform3DCrossAttn(BaseModule):
     """Graph-DETR4D 3D-offset cross-view attention (deform3d_cross_attn.py:33-339)."""
 

@@ -89,7 +89,7 @@ def _leaf(t):
     return t.clone().requires_grad_(True)
 
 
-@pytest.mark.parametrize("B,T,Q,P", [(1, 1, 96, 1), (2, 1, 40, 2)])
+@pytest.mark.parametrize("B,T,Q,P", [(1, 1, 96, 1), (2, 1, 40, 2), (1, 1, 24, 40)])
 def test_mode_a_backward(B, T, Q, P):
     sc = H.scene(B=B, T=T, Q=Q)
     logits = H.rand_inputs_a(sc, P=P)
