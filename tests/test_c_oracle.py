@@ -1,0 +1,35 @@
+"""The independent plain-C restatement (oracle/c/xview_ref.c) agrees with the torch oracle:
+mask bit-for-bit, values to 1e-5 (different summation order)."""
+import numpy as np
+import pytest
+import torch
+
+from graph_detr4d_b200 import synthetic as syn
+from oracle import c_ref, xview_oracle as xo
+from tests import helpers as H
+
+
+@pytest.mark.parametrize("B,T,P", [(1, 1, 1), (2, 2, 2)])
+def test_c_restatement_mode_a(B, T, P):
+    sc = H.scene(B=B, T=T, Q=60, C=64, shapes=[(12, 20), (6, 10), (3, 5), (2, 3)])
+    logits = H.rand_inputs_a(sc, P=P)
+    out_t, mask_t = xo.xview_a_core(sc["feats"], sc["ref"], logits, sc["l2i"], syn.PC_RANGE, 900, 1600)
+    out_c, mask_c = c_ref.forward(0, [f.numpy() for f in sc["feats"]], sc["ref"].numpy(), logits.numpy(),
+                                  sc["l2i"].numpy(), syn.PC_RANGE, 900.0, 1600.0, 2, P)
+    assert np.array_equal(mask_c.astype(bool), mask_t.numpy())
+    assert mask_t.any()
+    assert H.rel_err(torch.from_numpy(out_c), out_t) <= 1e-5
+
+
+@pytest.mark.parametrize("B,T,P", [(1, 2, 4), (2, 1, 3)])
+def test_c_restatement_mode_c(B, T, P):
+    sc = H.scene(B=B, T=T, Q=40, C=64, shapes=[(12, 20), (6, 10), (3, 5), (2, 3)])
+    logits, offsets, cam = H.rand_inputs_c(sc, Hh=2, P=P)
+    out_t, mask_t = xo.xview_c_core(sc["feats"], sc["ref"], offsets, logits, cam, sc["l2i"], syn.PC_RANGE,
+                                    900, 1600, 2)
+    out_c, mask_c = c_ref.forward(1, [f.numpy() for f in sc["feats"]], sc["ref"].numpy(), logits.numpy(),
+                                  sc["l2i"].numpy(), syn.PC_RANGE, 900.0, 1600.0, 2, P,
+                                  offsets=offsets.numpy(), cam_logits=cam.numpy())
+    assert np.array_equal(mask_c.astype(bool), mask_t[:, :, :, :, 0, :].numpy())
+    assert mask_t.any()
+    assert H.rel_err(torch.from_numpy(out_c), out_t) <= 1e-5
