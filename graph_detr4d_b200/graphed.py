@@ -23,6 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import modules
+from .glue import DeferredWgrad
 
 
 class GraphedTrainStep:
@@ -63,7 +64,9 @@ class GraphedTrainStep:
             for f in self.static_feats:
                 f.grad = None
             loss = forward_loss(self.static_feats)
-            loss.backward()
+            with DeferredWgrad() as wq:                    # weight grads of the small Linears: batched GEMMs
+                loss.backward()
+                wq.flush()
             if self.world > 1:
                 have = [(v, p.grad) for v, p in zip(self.flat_views, params) if p.grad is not None]
                 torch._foreach_copy_([v for v, _ in have], [g for _, g in have])

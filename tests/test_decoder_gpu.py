@@ -102,3 +102,31 @@ def test_cuda_graph_step_matches_eager():
     stepper.set_inputs([f * 0.5 for f in feats], metas)
     l_new = float(stepper.step())
     assert abs(l_new - l_g[1]) > 1e-6
+
+
+def test_deferred_batched_wgrad_matches_immediate():
+    from graph_detr4d_b200.glue import DeferredWgrad
+    sc = H.scene(B=1, T=1, Q=80)
+    model = _build("C", 6, 2).cuda()
+    feats = [f.cuda() for f in sc["feats"]]
+    gout = torch.randn(2, 80, 1, 256, generator=torch.Generator().manual_seed(5)).cuda()
+
+    def run(deferred):
+        g.clear_caches()
+        model.zero_grad(set_to_none=True)
+        st, _, _ = model([f.clone().requires_grad_(True) for f in feats], sc["metas"], 1)
+        loss = (st * gout).sum()
+        if deferred:
+            with DeferredWgrad() as wq:
+                loss.backward()
+                assert len(wq.items) > 20
+                wq.flush()
+        else:
+            loss.backward()
+        return {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    a, b = run(False), run(True)
+    assert a.keys() == b.keys() and len(a) > 60
+    for n in a:
+        assert a[n].shape == b[n].shape, n
+        assert H.rel_err(b[n], a[n]) <= 1e-4, n
