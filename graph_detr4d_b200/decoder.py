@@ -26,7 +26,7 @@ from typing import Callable, Optional, Sequence
 import torch
 import torch.nn as nn
 
-from .glue import fast_linear, self_attention
+from .glue import fast_layer_norm, fast_linear, self_attention
 from .modules import build_attention, inverse_sigmoid
 
 
@@ -71,11 +71,11 @@ class DecoderLayer(nn.Module):
         self.norms = nn.ModuleList([nn.LayerNorm(embed_dims) for _ in range(3)])
 
     def forward(self, query, value, query_pos, reference_points, img_metas):
-        query = self.norms[0](self.attentions[0](query, query_pos))
+        query = fast_layer_norm(self.attentions[0](query, query_pos), self.norms[0])
         query = self.attentions[1](query, None, value, None, query_pos=query_pos,
                                    reference_points=reference_points, img_metas=img_metas)
-        query = self.norms[1](query)
-        return self.norms[2](self.ffns[0](query))
+        query = fast_layer_norm(query, self.norms[1])
+        return fast_layer_norm(self.ffns[0](query), self.norms[2])
 
 
 class Detr3DTransformerDecoder(nn.Module):

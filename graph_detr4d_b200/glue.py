@@ -27,6 +27,7 @@ class DeferredWgrad:
 
     def __init__(self):
         self.items = []        # (weight_param, bias_param, row0, row1, g2, x2)
+        self.ln_items = []     # (weight_param, bias_param, g2, x2, mean, rstd)
 
     def __enter__(self):
         DeferredWgrad._active = self
@@ -65,6 +66,21 @@ class DeferredWgrad:
             if bp is not None:
                 bp.grad = gb if bp.grad is None else bp.grad + gb
         self.items.clear()
+        # LayerNorm gamma/beta: d_gamma = sum_rows g * xhat, d_beta = sum_rows g, batched by width
+        ln_groups = {}
+        for it in self.ln_items:
+            ln_groups.setdefault((it[2].shape[0], it[2].shape[1]), []).append(it)
+        for its in ln_groups.values():
+            G = torch.stack([it[2] for it in its])                     # (n, M, C)
+            X = torch.stack([it[3] for it in its])
+            mean = torch.stack([it[4] for it in its])                  # (n, M, 1)
+            rstd = torch.stack([it[5] for it in its])
+            dG = (G * ((X - mean) * rstd)).sum(1)                      # (n, C)
+            dB = G.sum(1)
+            for i, (wp, bp, *_rest) in enumerate(its):
+                wp.grad = dG[i] if wp.grad is None else wp.grad + dG[i]
+                bp.grad = dB[i] if bp.grad is None else bp.grad + dB[i]
+        self.ln_items.clear()
 
 
 class _FastLinearFn(torch.autograd.Function):
@@ -99,6 +115,41 @@ class _FastLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             db = (g2.new_ones(1, g2.shape[0]) @ g2).view(-1)
         return dx, dw, db, None
+
+
+class _FastLayerNormFn(torch.autograd.Function):
+    """LayerNorm whose gamma/beta gradients (a 12 us column reduction each, 30 per step) can be
+    deferred to one batched reduction (DeferredWgrad); dX is computed immediately."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, owner):
+        out, mean, rstd = torch.native_layer_norm(x, (x.shape[-1],), weight, bias, eps)
+        ctx.save_for_backward(x, mean, rstd, weight, bias)
+        ctx.owner = owner
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mean, rstd, weight, bias = ctx.saved_tensors
+        q = DeferredWgrad._active
+        g = g.contiguous()
+        if q is not None and ctx.owner is not None:
+            dx = torch.ops.aten.native_layer_norm_backward(g, x, (x.shape[-1],), mean, rstd, weight, bias,
+                                                           [True, False, False])[0]
+            C = x.shape[-1]
+            q.ln_items.append((*ctx.owner, g.reshape(-1, C), x.reshape(-1, C), mean.reshape(-1, 1),
+                               rstd.reshape(-1, 1)))
+            return dx, None, None, None, None
+        dx, dw, db = torch.ops.aten.native_layer_norm_backward(g, x, (x.shape[-1],), mean, rstd, weight, bias,
+                                                               [True, True, True])
+        return dx, dw, db, None, None
+
+
+def fast_layer_norm(x: torch.Tensor, ln: torch.nn.LayerNorm) -> torch.Tensor:
+    if not x.is_cuda or ln.weight is None or ln.bias is None or len(ln.normalized_shape) != 1:
+        return ln(x)
+    owner = (ln.weight, ln.bias) if ln.weight.requires_grad else None
+    return _FastLayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, owner)
 
 
 def fast_linear(x: torch.Tensor, lin: torch.nn.Linear) -> torch.Tensor:

@@ -48,7 +48,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .glue import fast_linear
+from .glue import fast_layer_norm, fast_linear
 from .ops import MODE_A, MODE_C, MODE_V2, PackedFeatures, XViewConfig
 
 import sys as _sys
@@ -234,7 +234,12 @@ def _img_hw(img_metas):
 
 def _run_position_encoder(seq: nn.Sequential, x):
     for m in seq:
-        x = fast_linear(x, m) if isinstance(m, nn.Linear) else m(x)
+        if isinstance(m, nn.Linear):
+            x = fast_linear(x, m)
+        elif isinstance(m, nn.LayerNorm):
+            x = fast_layer_norm(x, m)
+        else:
+            x = m(x)
     return x
 
 
