@@ -135,7 +135,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     // grad_out run owned by this lane (identical in every lane group)
     float g[PL];
     {
-      const float* go = WIDE ? p.grad_out + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.C
+      const float* go = WIDE ? p.grad_out + ((static_cast<size_t>(w.b) * p.Hh + w.h) * p.Q + w.q) * p.C
                              : p.grad_out + static_cast<size_t>(w.bq) * p.C + w.h * kHeadDim;
 #pragma unroll
       for (int j = 0; j < NV; ++j)
@@ -153,7 +153,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     constexpr int NR = PL / 4;
     float gr[NR][4];
     {
-      const float* go = WIDE ? p.grad_out + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.C
+      const float* go = WIDE ? p.grad_out + ((static_cast<size_t>(w.b) * p.Hh + w.h) * p.Q + w.q) * p.C
                              : p.grad_out + static_cast<size_t>(w.bq) * p.C + w.h * kHeadDim;
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
@@ -166,7 +166,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
       }
     }
     const float gws = (WIDE && p.grad_wsum != nullptr)
-                          ? __ldg(p.grad_wsum + static_cast<size_t>(w.bq) * p.Hh + w.h) : 0.f;
+                          ? __ldg(p.grad_wsum + (static_cast<size_t>(w.b) * p.Hh + w.h) * p.Q + w.q) : 0.f;
 
     if (MODE == GD4D_MODE_C) {
       head_softmax(p, w, sw);

@@ -116,7 +116,7 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
       for (int i = 0; i < PL; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
     }
     if (grp == 0) {
-      float* o = WIDE ? p.out + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.C
+      float* o = WIDE ? p.out + ((static_cast<size_t>(w.b) * p.Hh + w.h) * p.Q + w.q) * p.C
                       : p.out + static_cast<size_t>(w.bq) * p.C + w.h * kHeadDim;
 #pragma unroll
       for (int j = 0; j < NV; ++j)
@@ -128,7 +128,7 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     if (WIDE && p.wsum != nullptr) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) wsum_lane += __shfl_xor_sync(0xffffffffu, wsum_lane, o);
-      if (lane == 0) p.wsum[static_cast<size_t>(w.bq) * p.Hh + w.h] = wsum_lane;
+      if (lane == 0) p.wsum[(static_cast<size_t>(w.b) * p.Hh + w.h) * p.Q + w.q] = wsum_lane;
     }
     __syncwarp();  // the per-warp shared-memory lists are reused by the next work item
   }

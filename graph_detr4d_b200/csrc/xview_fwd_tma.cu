@@ -143,7 +143,7 @@ xview_fwd_tma_kernel(const __grid_constant__ gd4d_xview_params p, const int cand
         __syncwarp();                              // stage s (and, after the last batch, recs) reusable
       }
     }
-    float* o = p.out + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.C;
+    float* o = p.out + ((static_cast<size_t>(w.b) * p.Hh + w.h) * p.Q + w.q) * p.C;
 #pragma unroll
     for (int j = 0; j < NV; ++j)
 #pragma unroll
@@ -153,7 +153,7 @@ xview_fwd_tma_kernel(const __grid_constant__ gd4d_xview_params p, const int cand
     if (p.wsum != nullptr) {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) wsum_lane += __shfl_xor_sync(0xffffffffu, wsum_lane, off);
-      if (lane == 0) p.wsum[static_cast<size_t>(w.bq) * p.Hh + w.h] = wsum_lane;
+      if (lane == 0) p.wsum[(static_cast<size_t>(w.b) * p.Hh + w.h) * p.Q + w.q] = wsum_lane;
     }
     __syncwarp();
   }

@@ -47,7 +47,8 @@ class DeferredWgrad:
             G = torch.stack([it[4] for it in its])                     # (n, M, N)
             X = torch.stack([it[5] for it in its])                     # (n, M, K)
             dW = torch.bmm(G.transpose(1, 2), X)                       # (n, N, K)
-            dB = G.sum(1)                                              # (n, N)
+            ones = G.new_ones(1, 1, G.shape[1]).expand(G.shape[0], 1, G.shape[1])
+            dB = torch.bmm(ones, G).squeeze(1)                         # (n, N): GEMV, not aten::sum (2-CTA reduce)
             for i, (wp, bp, r0, r1, _, _) in enumerate(its):
                 whole = r0 == 0 and r1 == wp.shape[0]
                 if whole:
@@ -75,8 +76,9 @@ class DeferredWgrad:
             X = torch.stack([it[3] for it in its])
             mean = torch.stack([it[4] for it in its])                  # (n, M, 1)
             rstd = torch.stack([it[5] for it in its])
-            dG = (G * ((X - mean) * rstd)).sum(1)                      # (n, C)
-            dB = G.sum(1)
+            ones = G.new_ones(1, 1, G.shape[1]).expand(G.shape[0], 1, G.shape[1])
+            dG = torch.bmm(ones, G * ((X - mean) * rstd)).squeeze(1)   # (n, C)
+            dB = torch.bmm(ones, G).squeeze(1)
             for i, (wp, bp, *_rest) in enumerate(its):
                 wp.grad = dG[i] if wp.grad is None else wp.grad + dG[i]
                 bp.grad = dB[i] if bp.grad is None else bp.grad + dB[i]

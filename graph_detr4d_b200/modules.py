@@ -30,7 +30,7 @@ Differences from the reference, all deliberate:
   * Deform3DCrossAttn ``value_proj_mode`` (new): ``'fused'`` (default) never runs
     value_proj over the pixels.  By linearity sum_s w_s (W f_s + b) = W sum_s w_s f_s
     + b sum_s w_s, so each head gathers all C raw channels (kernel "wide" mode) and
-    W_v's head slice is applied to the (B,Q,Hh,C) result with one tiny batched GEMM.
+    W_v's head slice is applied to the (B,Hh,Q,C) result with one tiny batched GEMM.
     ``'dense'`` reproduces the reference's op boundary (value_proj GEMM over every
     pixel, then mmcv-layout head-slice sampling); it is used automatically when the
     channel count does not fit the wide kernel.
@@ -493,9 +493,10 @@ class Deform3DCrossAttn(BaseModule):
             agg, wsum = ops.xview_attention(cfg, packed, reference_points, logits, offsets, cam_logits, l2i)
             Hh, Ch = self.num_heads, self.embed_dims // self.num_heads
             wv = self.value_proj.weight.view(Hh, Ch, self.embed_dims)       # out channel = h*Ch + c
-            out = torch.einsum("bqhk,hck->bqhc", agg, wv) + \
-                wsum.unsqueeze(-1) * self.value_proj.bias.view(Hh, Ch)
-            out = out.flatten(2)                                            # (B,Q,C)
+            # agg is head-major (B,Hh,Q,C): one strided-batched GEMM, no transpose copy of the 7 MB aggregate
+            out = torch.matmul(agg, wv.transpose(1, 2)) + \
+                wsum.unsqueeze(-1) * self.value_proj.bias.view(Hh, 1, Ch)  # (B,Hh,Q,Ch)
+            out = out.permute(0, 2, 1, 3).flatten(2)                        # (B,Q,C)
         else:
             cfg = XViewConfig(MODE_C, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w)
             out = ops.xview_attention(cfg, packed, reference_points, logits, offsets, cam_logits, l2i,

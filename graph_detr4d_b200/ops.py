@@ -300,13 +300,13 @@ def _check_shapes(cfg, B, N, L, ref, attn_logits, offsets, cam_logits, lidar2img
 
 
 def _out_shape(cfg, B, Q, Cc):
-    return (B, Q, cfg.num_heads, Cc) if cfg.wide else (B, Q, Cc)
+    return (B, cfg.num_heads, Q, Cc) if cfg.wide else (B, Q, Cc)
 
 
 def xview_forward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
                   offsets=None, cam_logits=None, lidar2img=None, want_mask: bool = False):
     """One fused forward launch.
-    narrow: returns (out (B,Q,C), mask|None);  wide: returns ((out (B,Q,Hh,C), wsum (B,Q,Hh)), mask|None)."""
+    narrow: returns (out (B,Q,C), mask|None);  wide: returns ((out (B,Hh,Q,C), wsum (B,Hh,Q)), mask|None)."""
     for v in values:
         _require_cuda(v, "value")
     ref = _f32c(ref, "reference_points")
@@ -322,7 +322,7 @@ def xview_forward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: i
     p.out = out.data_ptr()
     wsum = None
     if cfg.wide:
-        wsum = torch.empty((B, Q, cfg.num_heads), device=ref.device, dtype=torch.float32)
+        wsum = torch.empty((B, cfg.num_heads, Q), device=ref.device, dtype=torch.float32)
         p.wsum = wsum.data_ptr()
     mask = None
     if want_mask:
@@ -398,7 +398,7 @@ def prepare_forward(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, li
     p.out = out.data_ptr()
     wsum = None
     if cfg.wide:
-        wsum = torch.empty((B, Q, cfg.num_heads), device=ref.device, dtype=torch.float32)
+        wsum = torch.empty((B, cfg.num_heads, Q), device=ref.device, dtype=torch.float32)
         p.wsum = wsum.data_ptr()
     pl = PreparedLaunch(_lib.load().gd4d_xview_forward, "gd4d_xview_forward", p, ref.device,
                         (list(values), ref, attn_logits, offsets, cam_logits, lidar2img, out, wsum))
@@ -492,7 +492,8 @@ def xview_attention(cfg: XViewConfig, packed: PackedFeatures, ref, attn_logits, 
                     cam_logits=None, lidar2img=None, values: Optional[Sequence[torch.Tensor]] = None):
     """Differentiable fused cross-view sampling attention.
 
-    narrow -> (B,Q,C) fp32;  wide -> (out (B,Q,Hh,C), wsum (B,Q,Hh)).
+    narrow -> (B,Q,C) fp32;  wide -> (out (B,Hh,Q,C), wsum (B,Hh,Q)): head-major, so the
+    per-head value_proj slices apply as one strided-batched GEMM without a transpose copy.
     ``values`` (differentiable channel-last tensors, e.g. the value_proj'ed maps of the
     dense path) override ``packed.levels``; without them the shared packed maps are
     sampled and their gradient goes to ``packed.sink``."""

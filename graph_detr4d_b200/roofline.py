@@ -62,7 +62,7 @@ def algorithmic_bytes(mode: int, stats: Dict[str, float], B: int, Q: int, N: int
     slice_bytes = 32 * elem_bytes
     if mode == MODE_C and wide:
         # gather-then-project: every corner read is a whole C-channel row, the output is
-        # (B,Q,Hh,C) (+ wsum), the feature gradient is a C-wide fp32 read-modify-write
+        # (B,Hh,Q,C) (+ wsum), the feature gradient is a C-wide fp32 read-modify-write
         S = stats["corner_reads_per_slice_group"]
         row = C * elem_bytes
         w_bytes = B * Q * num_heads * (L * P + 3 * P) * 4 + B * Q * N * 4

@@ -92,12 +92,12 @@ typedef enum gd4d_dtype { GD4D_F32 = 0, GD4D_BF16 = 1 } gd4d_dtype;
  * (deform3d_cross_attn.py:278) and then samples head h's 32-channel slice.  By
  * linearity  sum_s w_s * (W f_s + b) = W (sum_s w_s f_s) + b * sum_s w_s, so with
  * wide = 1 each head samples all C channels of the RAW feature maps:
- *   out  (B,Q,Hh,C) = sum_s w_s * bilinear(f_s)          (fp32)
- *   wsum (B,Q,Hh)   = sum_s w_s * (in-bounds corner weight sum)   [multiplies the bias]
+ *   out  (B,Hh,Q,C) = sum_s w_s * bilinear(f_s)          (fp32, head-major)
+ *   wsum (B,Hh,Q)   = sum_s w_s * (in-bounds corner weight sum)   [multiplies the bias]
  * and the caller applies W_v's head slice to `out` with one tiny batched GEMM.
  * No dense per-layer GEMM, no per-layer copy of the maps, and in backward the
  * feature gradient lands directly in ONE grad map shared by all decoder layers.
- * grad_out is then (B,Q,Hh,C) and grad_wsum (B,Q,Hh).  C must be 32 lanes * 16 B
+ * grad_out is then (B,Hh,Q,C) and grad_wsum (B,Hh,Q).  C must be 32 lanes * 16 B
  * * {1,2}: fp32 C in {128,256}, bf16 C in {256,512}.
  *
  * Backward (gd4d_xview_backward) reads grad_out (B,Q,C) and ACCUMULATES with

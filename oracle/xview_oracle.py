@@ -192,7 +192,7 @@ def xview_c_wide_core(feats, reference_points, offsets, attn_logits, cam_logits,
     """Gather-then-project restatement: every head samples ALL C raw channels with its
     own points/weights.  Built from ``xview_c_core`` itself (features repeated once per
     head, so head h's "slice" is the whole map) -- no new arithmetic.
-    Returns agg (B,Q,Hh,C) and wsum (B,Q,Hh) = the same sampling of an all-ones map
+    Returns agg (B,Hh,Q,C) and wsum (B,Hh,Q) (head-major, the product's layout) = the same sampling of an all-ones map
     (zeros outside the image), which is what multiplies value_proj's bias:
         sum_s w_s (W f_s + b) = W agg + b wsum      (deform3d_cross_attn.py:278-324)."""
     B, Q = reference_points.shape[:2]
@@ -203,7 +203,7 @@ def xview_c_wide_core(feats, reference_points, offsets, attn_logits, cam_logits,
     ones = [torch.ones_like(f[:, :, :1]).repeat(1, 1, num_heads, 1, 1) for f in feats]
     wsum, _ = xview_c_core(ones, reference_points, offsets, attn_logits, cam_logits, lidar2img,
                            pc_range, img_h, img_w, num_heads)
-    return agg.view(B, Q, num_heads, C), wsum.view(B, Q, num_heads)
+    return agg.view(B, Q, num_heads, C).transpose(1, 2), wsum.view(B, Q, num_heads).transpose(1, 2)
 
 
 # --------------------------------------------------------------------------

@@ -188,8 +188,8 @@ def test_mode_c_wide_forward_backward(C, dtype, T, Q):
     sc = H.scene(B=1, T=T, Q=Q, C=C)
     logits, offsets, cam = H.rand_inputs_c(sc, P=4)
     g = torch.Generator().manual_seed(10)
-    g1 = torch.randn(1, Q, 8, C, generator=g)
-    g2 = torch.randn(1, Q, 8, generator=g)
+    g1 = torch.randn(1, 8, Q, C, generator=g)
+    g2 = torch.randn(1, 8, Q, generator=g)
     feats_src = [f.to(dtype).float() for f in sc["feats"]]
     feats_o = [_leaf(f) for f in feats_src]
     ref_o, log_o, off_o, cam_o = _leaf(sc["ref"]), _leaf(logits), _leaf(offsets), _leaf(cam)
@@ -203,7 +203,7 @@ def test_mode_c_wide_forward_backward(C, dtype, T, Q):
     assert packed.token is not None and packed.levels[0].dtype == dtype
     cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=True)
     agg, ws = ops.xview_attention(cfg, packed, ref_g, log_g, off_g, cam_g, sc["l2i"].cuda())
-    assert tuple(agg.shape) == (1, Q, 8, C) and tuple(ws.shape) == (1, Q, 8)
+    assert tuple(agg.shape) == (1, 8, Q, C) and tuple(ws.shape) == (1, 8, Q)
     ((agg * g1.cuda()).sum() + (ws * g2.cuda()).sum()).backward()
     assert H.rel_err(agg.detach().cpu(), agg_o.detach()) <= FWD_TOL
     assert H.rel_err(ws.detach().cpu(), ws_o.detach()) <= FWD_TOL

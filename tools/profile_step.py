@@ -13,10 +13,12 @@ opt = torch.optim.AdamW(model.parameters(), lr=2e-4, fused=True, capturable=True
 feats = [f.to(dev).requires_grad_(True) for f in syn.make_feats(1, 6 * T, 256, syn.LEVEL_SHAPES_928x1600)]
 metas = syn.make_img_metas(1, T)
 
+from graph_detr4d_b200.glue import DeferredWgrad
 def step():
     modules.clear_pack_cache()
     st, _, refs = model(feats, metas, 1)
-    bench.loss_fn(st, refs).backward()
+    with DeferredWgrad() as wq:
+        bench.loss_fn(st, refs).backward(); wq.flush()
     opt.step(); opt.zero_grad(set_to_none=True)
     for f in feats: f.grad = None
 
@@ -29,5 +31,5 @@ ev = [e for e in prof.key_averages() if e.device_time_total > 0 or getattr(e, "s
 rows = sorted(((e.self_device_time_total / 3.0, e.count / 3, e.key) for e in prof.key_averages() if e.self_device_time_total > 0), reverse=True)
 tot = sum(r[0] for r in rows)
 print(f"total device time per step: {tot/1e3:.3f} ms")
-for t, n, k in rows[:28]:
+for t, n, k in rows[:45]:
     print(f"{t:9.1f} us {100*t/tot:5.1f}% n={n:6.1f} {k[:110]}")
