@@ -111,7 +111,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                 "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                 text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -299,10 +299,10 @@ def main():
         return ms
 
     W, K = max(args.warmup, 3), args.steps
+    sampler = ClockSampler(local_rank)                      # 200 ms period (B200_PROFILING.md): started before
+    sampler.start()                                         # the warm-up so short timed regions still get samples
     for _ in range(W):
         step_resident()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ms_total = timed(step_resident, K)
     launches = launches_per_step * K
     e2e_state.update(i=0, n=2)
@@ -383,8 +383,8 @@ def kernel_roofline(model, feats_dev, metas, T, dtype, dev):
                                             HEADS, POINTS)
         eb = 2 if sets[0][0].dtype == torch.bfloat16 else 4
         ab = roofline.algorithmic_bytes(MODE_C, stats, 1, Q, N, C, HEADS, LEVELS, POINTS, eb, wide=wide)
-        gout = torch.randn((1, Q, HEADS, C) if wide else (1, Q, C), device=dev)
-        gws = torch.randn(1, Q, HEADS, device=dev) if wide else None
+        gout = torch.randn((1, HEADS, Q, C) if wide else (1, Q, C), device=dev)
+        gws = torch.randn(1, HEADS, Q, device=dev) if wide else None
         gsets = [[torch.zeros(v.shape, device=dev, dtype=torch.float32) for v in s] for s in sets]
         reps = 60
 

@@ -1,4 +1,4 @@
-"""ctypes binding of libgd4d_xview.so (the C ABI in include/gd4d_xview.h).
+"""ctypes binding of libgd4d_xview.so (the C ABI in include/gd4d_xview.h and gd4d_glue.h).
 
 There is deliberately NO fallback: if the shared library is missing or was not
 built for this GPU, every op raises.  ``load()`` builds in-tree with nvcc when the
@@ -27,6 +27,13 @@ EXPORTS = (
     "gd4d_xview_forward",
     "gd4d_xview_backward",
     "gd4d_pack_nchw",
+    # include/gd4d_glue.h
+    "gd4d_inverse_sigmoid_fwd",
+    "gd4d_inverse_sigmoid_bwd",
+    "gd4d_ref_update",
+    "gd4d_bias_act",
+    "gd4d_add_layernorm_fwd",
+    "gd4d_add_layernorm_bwd",
 )
 
 
@@ -109,6 +116,16 @@ def load(build_if_missing: bool = True):
         lib.gd4d_pack_nchw.restype = C.c_int
         lib.gd4d_pack_nchw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+        for name, args in (
+                ("gd4d_inverse_sigmoid_fwd", [vp, vp, i64, f32, i32, vp]),
+                ("gd4d_inverse_sigmoid_bwd", [vp, vp, vp, i64, f32, i32, vp]),
+                ("gd4d_ref_update", [vp, i32, vp, vp, i64, f32, vp]),
+                ("gd4d_bias_act", [vp, vp, i64, i32, i32, vp]),
+                ("gd4d_add_layernorm_fwd", [vp] * 10 + [i64, i32, f32, i32, vp]),
+                ("gd4d_add_layernorm_bwd", [vp] * 8 + [i64, i32, i32, vp])):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = C.c_int, args
         lib.gd4d_params_size.restype = C.c_int
         lib.gd4d_params_size.argtypes = []
         if lib.gd4d_abi_version() != ABI_VERSION:

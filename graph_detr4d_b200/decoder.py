@@ -26,8 +26,31 @@ from typing import Callable, Optional, Sequence
 import torch
 import torch.nn as nn
 
-from .glue import fast_layer_norm, fast_linear, self_attention
+from . import fused
+from .glue import can_defer_bias, fast_layer_norm, fast_linear, linear_relu, self_attention
 from .modules import build_attention, inverse_sigmoid
+
+
+def _dropout_active(m: nn.Module) -> bool:
+    return isinstance(m, nn.Dropout) and m.training and m.p > 0
+
+
+def _run_branch(seq: nn.Sequential, x):
+    """Linear(-ReLU)* chain of a regression branch; Linear+ReLU pairs run as GEMM + one launch."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, nn.Linear):
+            if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+                x = linear_relu(x, m)
+                i += 1
+            else:
+                x = fast_linear(x, m)
+        else:
+            x = m(x)
+        i += 1
+    return x
 
 
 class SelfAttention(nn.Module):
@@ -38,14 +61,25 @@ class SelfAttention(nn.Module):
         self.attn = nn.MultiheadAttention(embed_dims, num_heads, dropout)
         self.dropout_layer = nn.Dropout(dropout)
 
-    def forward(self, query, query_pos=None):
-        identity = query
+    def branch(self, query, query_pos=None, defer_bias=False):
+        """dropout(attention(query)) without the identity.  ``defer_bias``: returns
+        ``(out_without_out_proj_bias, bias)`` for a consumer that adds the bias itself (only when
+        dropout is inactive, else ``(out, None)``)."""
         if query.is_cuda:
-            out = self_attention(query, query_pos, self.attn)          # bmm+softmax path (glue.py)
+            defer = defer_bias and not _dropout_active(self.dropout_layer) and \
+                can_defer_bias(query, self.attn.out_proj)
+            out = self_attention(query, query_pos, self.attn, out_bias=not defer)   # bmm+softmax path (glue.py)
+            if defer_bias:
+                return (out, self.attn.out_proj.bias) if defer else (self.dropout_layer(out), None)
         else:
             q = k = query if query_pos is None else query + query_pos
             out = self.attn(q, k, value=query, need_weights=False)[0]
-        return identity + self.dropout_layer(out)
+            if defer_bias:
+                return self.dropout_layer(out), None
+        return self.dropout_layer(out)
+
+    def forward(self, query, query_pos=None):
+        return query + self.branch(query, query_pos)
 
 
 class FFN(nn.Module):
@@ -57,9 +91,17 @@ class FFN(nn.Module):
             nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True), nn.Dropout(ffn_drop)),
             nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
 
+    def branch(self, x, defer_bias=False):
+        h = self.layers[0][2](linear_relu(x, self.layers[0][0]))
+        lin2 = self.layers[1]
+        if defer_bias:
+            if not _dropout_active(self.layers[2]) and can_defer_bias(h, lin2):
+                return fast_linear(h, lin2, add_bias=False), lin2.bias
+            return self.layers[2](fast_linear(h, lin2)), None
+        return self.layers[2](fast_linear(h, lin2))
+
     def forward(self, x):
-        h = self.layers[0][2](self.layers[0][1](fast_linear(x, self.layers[0][0])))
-        return x + self.layers[2](fast_linear(h, self.layers[1]))
+        return x + self.branch(x)
 
 
 class DecoderLayer(nn.Module):
@@ -71,11 +113,24 @@ class DecoderLayer(nn.Module):
         self.norms = nn.ModuleList([nn.LayerNorm(embed_dims) for _ in range(3)])
 
     def forward(self, query, value, query_pos, reference_points, img_metas):
-        query = fast_layer_norm(self.attentions[0](query, query_pos), self.norms[0])
-        query = self.attentions[1](query, None, value, None, query_pos=query_pos,
-                                   reference_points=reference_points, img_metas=img_metas)
-        query = fast_layer_norm(query, self.norms[1])
-        return fast_layer_norm(self.ffns[0](query), self.norms[2])
+        # post-norm layer: every "branch + identity" sum is folded into the LayerNorm that
+        # follows it (fused.add_layernorm: one launch) when the tensors are CUDA fp32
+        fuse = all(fused.can_fuse_layernorm(query, n) for n in self.norms)
+        cross = self.attentions[1]
+        if not (fuse and hasattr(cross, "forward_parts")):
+            query = fast_layer_norm(self.attentions[0](query, query_pos), self.norms[0])
+            query = cross(query, None, value, None, query_pos=query_pos,
+                          reference_points=reference_points, img_metas=img_metas)
+            query = fast_layer_norm(query, self.norms[1])
+            return fast_layer_norm(self.ffns[0](query), self.norms[2])
+        out, bias = self.attentions[0].branch(query, query_pos, defer_bias=True)
+        query = fused.add_layernorm(out, self.norms[0], query, xbias=bias)
+        out, res, pos, bias = cross.forward_parts(query, None, value, None, query_pos=query_pos,
+                                                  reference_points=reference_points, img_metas=img_metas,
+                                                  defer_bias=True)
+        query = fused.add_layernorm(out, self.norms[1], res, pos, xbias=bias)
+        out, bias = self.ffns[0].branch(query, defer_bias=True)
+        return fused.add_layernorm(out, self.norms[2], query, xbias=bias)
 
 
 class Detr3DTransformerDecoder(nn.Module):
@@ -97,12 +152,14 @@ class Detr3DTransformerDecoder(nn.Module):
             output = layer(output, value, query_pos, reference_points, img_metas)
             if reg_branches is not None:                                    # :201-214
                 tmp = output.permute(1, 0, 2)
-                for m in reg_branches[lid]:
-                    tmp = fast_linear(tmp, m) if isinstance(m, nn.Linear) else m(tmp)
-                new_ref = torch.zeros_like(reference_points)
-                new_ref[..., :2] = tmp[..., :2] + inverse_sigmoid(reference_points[..., :2])
-                new_ref[..., 2:3] = tmp[..., 4:5] + inverse_sigmoid(reference_points[..., 2:3])
-                reference_points = new_ref.sigmoid().detach()
+                tmp = _run_branch(reg_branches[lid], tmp)
+                if fused.ENABLED and tmp.is_cuda and tmp.dtype == torch.float32:
+                    reference_points = fused.ref_update(tmp, reference_points)      # one launch
+                else:
+                    new_ref = torch.zeros_like(reference_points)
+                    new_ref[..., :2] = tmp[..., :2] + inverse_sigmoid(reference_points[..., :2])
+                    new_ref[..., 2:3] = tmp[..., 4:5] + inverse_sigmoid(reference_points[..., 2:3])
+                    reference_points = new_ref.sigmoid().detach()
             if self.return_intermediate:
                 intermediate.append(output)
                 intermediate_ref.append(reference_points)

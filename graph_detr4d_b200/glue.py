@@ -92,19 +92,60 @@ class _FastLinearFn(torch.autograd.Function):
     slices of) leaf Parameters."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, owner=None):
+    def forward(ctx, x, weight, bias, owner=None, add_bias=True):
+        """``add_bias=False``: the GEMM runs without its bias epilogue (a separate kernel in fp32
+        cuBLAS) because the consumer adds the bias itself (fused.add_layernorm ``xbias``); the
+        bias gradient is still produced here -- it is the column sum of the same ``g``."""
         x2 = x.reshape(-1, x.shape[-1])
         ctx.save_for_backward(x2, weight)
         ctx.xshape = x.shape
         ctx.owner = owner
         y = x.new_empty(*x.shape[:-1], weight.shape[0])       # final shape: not a view, so a
-        torch.addmm(bias, x2, weight.t(), out=y.view(-1, weight.shape[0]))   # following in-place ReLU is legal
+        if add_bias:                                          # following in-place ReLU is legal
+            torch.addmm(bias, x2, weight.t(), out=y.view(-1, weight.shape[0]))
+        else:
+            torch.mm(x2, weight.t(), out=y.view(-1, weight.shape[0]))
         return y
 
     @staticmethod
     def backward(ctx, g):
         x2, weight = ctx.saved_tensors
         g2 = g.reshape(-1, g.shape[-1])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (g2 @ weight).view(ctx.xshape)
+        q = DeferredWgrad._active
+        if q is not None and ctx.owner is not None and ctx.needs_input_grad[1]:
+            q.items.append((*ctx.owner, g2, x2))
+            return dx, None, None, None, None
+        if ctx.needs_input_grad[1]:
+            dw = g2.t() @ x2
+        if ctx.needs_input_grad[2]:
+            db = (g2.new_ones(1, g2.shape[0]) @ g2).view(-1)
+        return dx, dw, db, None, None
+
+
+class _LinearReluFn(torch.autograd.Function):
+    """relu(F.linear(x)) as GEMM + ONE in-place bias+ReLU launch (gd4d_bias_act) instead of
+    GEMM + cuBLAS bias epilogue kernel + ReLU kernel; backward masks the gradient once and then
+    behaves like _FastLinearFn (deferred batched weight/bias gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, owner=None):
+        from . import fused
+        x2 = x.reshape(-1, x.shape[-1])
+        y = x.new_empty(*x.shape[:-1], weight.shape[0])
+        torch.mm(x2, weight.t(), out=y.view(-1, weight.shape[0]))
+        fused.bias_act_(y, bias, relu=True)
+        ctx.save_for_backward(x2, weight, y)
+        ctx.xshape = x.shape
+        ctx.owner = owner
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, weight, y = ctx.saved_tensors
+        g2 = torch.ops.aten.threshold_backward(g, y, 0).reshape(-1, g.shape[-1])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = (g2 @ weight).view(ctx.xshape)
@@ -154,14 +195,61 @@ def fast_layer_norm(x: torch.Tensor, ln: torch.nn.LayerNorm) -> torch.Tensor:
     return _FastLayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, owner)
 
 
-def fast_linear(x: torch.Tensor, lin: torch.nn.Linear) -> torch.Tensor:
+def fast_linear(x: torch.Tensor, lin: torch.nn.Linear, add_bias: bool = True) -> torch.Tensor:
     if lin.bias is None or not x.is_cuda or x.dtype != lin.weight.dtype:
+        assert add_bias, "deferred bias needs the CUDA path"
         return torch.nn.functional.linear(x, lin.weight, lin.bias)
     owner = (lin.weight, lin.bias, 0, lin.weight.shape[0]) if lin.weight.requires_grad else None
-    return _FastLinearFn.apply(x, lin.weight, lin.bias, owner)
+    return _FastLinearFn.apply(x, lin.weight, lin.bias, owner, add_bias)
 
 
-def self_attention(query, query_pos, mha: torch.nn.MultiheadAttention):
+def can_defer_bias(x: torch.Tensor, lin: torch.nn.Linear) -> bool:
+    return lin.bias is not None and x.is_cuda and x.dtype == lin.weight.dtype == torch.float32
+
+
+def linear_relu(x: torch.Tensor, lin: torch.nn.Linear) -> torch.Tensor:
+    """relu(lin(x)); on CUDA fp32 the bias and the ReLU are one in-place launch after the GEMM."""
+    from . import fused
+    if not (fused.ENABLED and can_defer_bias(x, lin) and lin.out_features % 4 == 0):
+        return torch.relu_(fast_linear(x, lin))
+    owner = (lin.weight, lin.bias, 0, lin.weight.shape[0]) if lin.weight.requires_grad else None
+    return _LinearReluFn.apply(x, lin.weight, lin.bias, owner)
+
+
+_ZEROS = {}
+
+
+def _zero(like: torch.Tensor) -> torch.Tensor:
+    """A persistent (1,1,1) zero per device/dtype: baddbmm's ignored ``input`` (beta = 0) without
+    a fill launch per call."""
+    key = (like.device, like.dtype)
+    z = _ZEROS.get(key)
+    if z is None:
+        with torch.no_grad():
+            z = _ZEROS[key] = torch.zeros(1, 1, 1, device=like.device, dtype=like.dtype)
+    return z
+
+
+class _ScaledBmmNT(torch.autograd.Function):
+    """alpha * q @ k^T with alpha folded into the GEMMs (forward and both backward GEMMs): no
+    separate elementwise scale of q (forward) or of its gradient (backward)."""
+
+    @staticmethod
+    def forward(ctx, q, k, alpha: float):
+        ctx.save_for_backward(q, k)
+        ctx.alpha = alpha
+        return torch.baddbmm(_zero(q), q, k.transpose(1, 2), beta=0.0, alpha=alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k = ctx.saved_tensors
+        z = _zero(g)
+        dq = torch.baddbmm(z, g, k, beta=0.0, alpha=ctx.alpha) if ctx.needs_input_grad[0] else None
+        dk = torch.baddbmm(z, g.transpose(1, 2), q, beta=0.0, alpha=ctx.alpha) if ctx.needs_input_grad[1] else None
+        return dq, dk, None
+
+
+def self_attention(query, query_pos, mha: torch.nn.MultiheadAttention, out_bias: bool = True):
     """nn.MultiheadAttention(q=k=query+pos, v=query), batch_first=False, eval/dropout-free
     math: explicit bmm + softmax (faster than the flash/mem-efficient kernels at L=900,
     head_dim 32, fp32).  Uses the module's own packed parameters."""
@@ -171,14 +259,14 @@ def self_attention(query, query_pos, mha: torch.nn.MultiheadAttention):
     w, b = mha.in_proj_weight, mha.in_proj_bias
     qk_in = query if query_pos is None else query + query_pos
     own = w.requires_grad
-    qk = _FastLinearFn.apply(qk_in, w[:2 * E], b[:2 * E], (w, b, 0, 2 * E) if own else None)        # (L,B,2E)
-    v = _FastLinearFn.apply(query, w[2 * E:], b[2 * E:], (w, b, 2 * E, 3 * E) if own else None)    # (L,B,E)
+    qk = _FastLinearFn.apply(qk_in, w[:2 * E], b[:2 * E], (w, b, 0, 2 * E) if own else None, True)  # (L,B,2E)
+    v = _FastLinearFn.apply(query, w[2 * E:], b[2 * E:], (w, b, 2 * E, 3 * E) if own else None, True)  # (L,B,E)
     q, k = qk[..., :E], qk[..., E:]
     q = q.reshape(L, B * H, d).transpose(0, 1)                          # (B*H,L,d)
     k = k.reshape(L, B * H, d).transpose(0, 1)
     v = v.reshape(L, B * H, d).transpose(0, 1)
-    attn = torch.bmm(q * (1.0 / math.sqrt(d)), k.transpose(1, 2)).softmax(-1)
+    attn = _ScaledBmmNT.apply(q, k, 1.0 / math.sqrt(d)).softmax(-1)
     if mha.dropout > 0 and mha.training:
         attn = torch.nn.functional.dropout(attn, mha.dropout)
     out = torch.bmm(attn, v).transpose(0, 1).reshape(L, B, E)
-    return fast_linear(out, mha.out_proj)
+    return fast_linear(out, mha.out_proj, add_bias=out_bias)

@@ -47,8 +47,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
-from .glue import fast_layer_norm, fast_linear
+from . import fused, ops
+from .glue import can_defer_bias, fast_layer_norm, fast_linear
 from .ops import MODE_A, MODE_C, MODE_V2, PackedFeatures, XViewConfig
 
 import sys as _sys
@@ -233,14 +233,48 @@ def _img_hw(img_metas):
 
 
 def _run_position_encoder(seq: nn.Sequential, x):
-    for m in seq:
+    """Linear-LN-ReLU-Linear-LN-ReLU; on CUDA fp32 every LN+ReLU pair is one fused launch."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
         if isinstance(m, nn.Linear):
-            x = fast_linear(x, m)
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if (isinstance(nxt, nn.LayerNorm) and can_defer_bias(x, m) and nxt.normalized_shape == (m.out_features,)
+                    and fused.can_fuse_layernorm(x.new_empty(0, m.out_features), nxt)):
+                # Linear -> LN (-> ReLU): GEMM without epilogue, bias + LN (+ ReLU) in one launch
+                relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+                x = fused.add_layernorm(fast_linear(x, m, add_bias=False), nxt, relu=relu, xbias=m.bias)
+                i += 2 if relu else 1
+            else:
+                x = fast_linear(x, m)
         elif isinstance(m, nn.LayerNorm):
-            x = fast_layer_norm(x, m)
+            relu_next = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+            if relu_next and fused.can_fuse_layernorm(x, m):
+                x = fused.add_layernorm(x, m, relu=True)
+                i += 1
+            else:
+                x = fast_layer_norm(x, m)
         else:
             x = m(x)
+        i += 1
     return x
+
+
+def _output_proj(x, lin: nn.Linear, dropout: nn.Module, defer_bias: bool):
+    """dropout(lin(x)) -> (tensor, pending_bias).  The bias is left to the caller (one launch less:
+    fp32 cuBLAS runs the bias epilogue as its own kernel) only when asked and dropout is inactive."""
+    active = isinstance(dropout, nn.Dropout) and dropout.training and dropout.p > 0
+    if defer_bias and fused.ENABLED and not active and can_defer_bias(x, lin):
+        return fast_linear(x, lin, add_bias=False), lin.bias
+    return dropout(fast_linear(x, lin)), None
+
+
+def _inv_sigmoid(x, clamp_max=False):
+    """inverse_sigmoid as one launch on the path (CUDA fp32); the op-by-op torch version otherwise."""
+    if fused.ENABLED and x.is_cuda and x.dtype == torch.float32:
+        return fused.inverse_sigmoid(x, 1e-5, clamp_max)
+    return inverse_sigmoid(x, clamp_max=clamp_max)
 
 
 def _position_encoder(in_dims, embed_dims):
@@ -290,6 +324,19 @@ class Detr3DCrossAtten(BaseModule):
 
     def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
+        out, inp_residual, pos_feat = self.forward_parts(
+            query, key, value, residual, query_pos=query_pos, key_padding_mask=key_padding_mask,
+            reference_points=reference_points, spatial_shapes=spatial_shapes,
+            level_start_index=level_start_index, **kwargs)
+        return out + inp_residual + pos_feat
+
+    def forward_parts(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
+                      reference_points=None, spatial_shapes=None, level_start_index=None,
+                      defer_bias=False, **kwargs):
+        """The three addends of ``forward`` -- dropout(output_proj(sampled)), the residual and the
+        position feature -- so that a caller that owns the following LayerNorm (decoder.py) can
+        fold the sum into it (one launch).  With ``defer_bias`` a 4th item is returned: the
+        output_proj bias still to be added to the first addend (or None if it already was)."""
         if key is None:
             key = query
         if value is None:
@@ -308,9 +355,9 @@ class Detr3DCrossAtten(BaseModule):
         cfg = XViewConfig(MODE_A, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w)
         l2i = _L2I_CACHE.get(img_metas, query.device)
         out = ops.xview_attention(cfg, packed, reference_points, logits, lidar2img=l2i)   # (B,Q,C)
-        out = fast_linear(out.permute(1, 0, 2), self.output_proj)
-        pos_feat = _run_position_encoder(self.position_encoder, inverse_sigmoid(reference_points)).permute(1, 0, 2)
-        return self.dropout(out) + inp_residual + pos_feat
+        out, pending = _output_proj(out.permute(1, 0, 2), self.output_proj, self.dropout, defer_bias)
+        pos_feat = _run_position_encoder(self.position_encoder, _inv_sigmoid(reference_points)).permute(1, 0, 2)
+        return (out, inp_residual, pos_feat, pending) if defer_bias else (out, inp_residual, pos_feat)
 
 
 # ----------------------------------------------------------------------------------------
@@ -365,6 +412,19 @@ class Detr3DCrossAttenV2(BaseModule):
 
     def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
+        out, inp_residual, pos_feat = self.forward_parts(
+            query, key, value, residual, query_pos=query_pos, key_padding_mask=key_padding_mask,
+            reference_points=reference_points, spatial_shapes=spatial_shapes,
+            level_start_index=level_start_index, **kwargs)
+        return out + inp_residual + pos_feat
+
+    def forward_parts(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
+                      reference_points=None, spatial_shapes=None, level_start_index=None,
+                      defer_bias=False, **kwargs):
+        """The three addends of ``forward`` -- dropout(output_proj(sampled)), the residual and the
+        position feature -- so that a caller that owns the following LayerNorm (decoder.py) can
+        fold the sum into it (one launch).  With ``defer_bias`` a 4th item is returned: the
+        output_proj bias still to be added to the first addend (or None if it already was)."""
         if key is None:
             key = query
         if value is None:
@@ -384,9 +444,9 @@ class Detr3DCrossAttenV2(BaseModule):
         cfg = XViewConfig(MODE_V2, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w)
         l2i = _L2I_CACHE.get(img_metas, query.device)
         out = ops.xview_attention(cfg, packed, reference_points, logits, offsets, None, l2i)   # (B,Q,C)
-        out = fast_linear(out.permute(1, 0, 2), self.output_proj)
-        pos_feat = _run_position_encoder(self.position_encoder, inverse_sigmoid(reference_points)).permute(1, 0, 2)
-        return self.dropout(out) + inp_residual + pos_feat
+        out, pending = _output_proj(out.permute(1, 0, 2), self.output_proj, self.dropout, defer_bias)
+        pos_feat = _run_position_encoder(self.position_encoder, _inv_sigmoid(reference_points)).permute(1, 0, 2)
+        return (out, inp_residual, pos_feat, pending) if defer_bias else (out, inp_residual, pos_feat)
 
 
 # ----------------------------------------------------------------------------------------
@@ -469,6 +529,19 @@ class Deform3DCrossAttn(BaseModule):
 
     def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
+        out, inp_residual, pos_feat = self.forward_parts(
+            query, key, value, residual, query_pos=query_pos, key_padding_mask=key_padding_mask,
+            reference_points=reference_points, spatial_shapes=spatial_shapes,
+            level_start_index=level_start_index, **kwargs)
+        return out + inp_residual + pos_feat
+
+    def forward_parts(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
+                      reference_points=None, spatial_shapes=None, level_start_index=None,
+                      defer_bias=False, **kwargs):
+        """The three addends of ``forward`` -- dropout(output_proj(sampled)), the residual and the
+        position feature -- so that a caller that owns the following LayerNorm (decoder.py) can
+        fold the sum into it (one launch).  With ``defer_bias`` a 4th item is returned: the
+        output_proj bias still to be added to the first addend (or None if it already was)."""
         if key is None:
             key = query
         if value is None:
@@ -494,17 +567,23 @@ class Deform3DCrossAttn(BaseModule):
             Hh, Ch = self.num_heads, self.embed_dims // self.num_heads
             wv = self.value_proj.weight.view(Hh, Ch, self.embed_dims)       # out channel = h*Ch + c
             # agg is head-major (B,Hh,Q,C): one strided-batched GEMM, no transpose copy of the 7 MB aggregate
-            out = torch.matmul(agg, wv.transpose(1, 2)) + \
-                wsum.unsqueeze(-1) * self.value_proj.bias.view(Hh, 1, Ch)  # (B,Hh,Q,Ch)
-            out = out.permute(0, 2, 1, 3).flatten(2)                        # (B,Q,C)
+            # W_v agg + b wsum as GEMMs only: the bias term is a K=1 batched GEMM folded into the main
+            # one by baddbmm, so neither forward nor backward needs elementwise / reduction launches
+            Bq, Qn = agg.shape[0], agg.shape[2]
+            wt = wv.transpose(1, 2).unsqueeze(0).expand(Bq, Hh, self.embed_dims, Ch).reshape(Bq * Hh, self.embed_dims, Ch)
+            bv = self.value_proj.bias.view(1, Hh, 1, Ch).expand(Bq, Hh, 1, Ch).reshape(Bq * Hh, 1, Ch)
+            out = torch.baddbmm(torch.bmm(wsum.reshape(Bq * Hh, Qn, 1), bv),
+                                agg.reshape(Bq * Hh, Qn, self.embed_dims), wt)   # (B*Hh,Q,Ch)
+            out = out.view(Bq, Hh, Qn, Ch).permute(0, 2, 1, 3).flatten(2)       # (B,Q,C)
         else:
             cfg = XViewConfig(MODE_C, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w)
             out = ops.xview_attention(cfg, packed, reference_points, logits, offsets, cam_logits, l2i,
                                       values=self.project_values(packed))  # (B,Q,C)
-        out = fast_linear(out, self.output_proj).permute(1, 0, 2)
+        out, pending = _output_proj(out, self.output_proj, self.dropout, defer_bias)
+        out = out.permute(1, 0, 2)
         r3d = reference_points
         if self.depth_encode:
             depth = (r3d[..., 0:1] ** 2 + r3d[..., 1:2] ** 2) ** 0.5
             r3d = torch.cat([r3d, depth], dim=-1)
-        pos_feat = _run_position_encoder(self.position_encoder, inverse_sigmoid(r3d, clamp_max=True)).permute(1, 0, 2)
-        return self.dropout(out) + inp_residual + pos_feat
+        pos_feat = _run_position_encoder(self.position_encoder, _inv_sigmoid(r3d, clamp_max=True)).permute(1, 0, 2)
+        return (out, inp_residual, pos_feat, pending) if defer_bias else (out, inp_residual, pos_feat)

@@ -1,0 +1,73 @@
+/*
+ * gd4d_glue.h -- C ABI of the small fused kernels that sit either side of the
+ * cross-view sampling kernels inside one decoder layer.
+ *
+ * The reference spells these as chains of 5-20 one-line torch ops on (B*Q, 3) or
+ * (B*Q, 256) tensors; at B*Q = 900 every one of them is a launch-latency-bound
+ * kernel.  Each entry point below is ONE launch.  Same conventions as
+ * gd4d_xview.h: plain C, raw fp32 DEVICE pointers, CUDA stream as void*, no
+ * allocation, no synchronisation, 0 or a negative gd4d_status.
+ *
+ * Reference lines replaced (projects/mmdet3d_plugin/models/utils/):
+ *   gd4d_inverse_sigmoid_fwd/bwd  inverse_sigmoid, detr3d_transformer.py:28-43 and
+ *                                 deform3d_cross_attn.py:16-31 (the latter also clamps to max=1)
+ *   gd4d_ref_update               reference-point refinement in logit space,
+ *                                 detr3d_transformer.py:201-214
+ *   gd4d_bias_act                 Linear bias (+ReLU) epilogue: FFN Linear-ReLU (mmcv FFN), the
+ *                                 regression branches' Linear-ReLU (detr3d_head.py:72-95)
+ *   gd4d_add_layernorm_fwd/bwd    "x (+ residual (+ pos_feat)) -> LayerNorm (-> ReLU)":
+ *                                 the post-norm residual sums of the decoder layer
+ *                                 (operation_order self_attn,norm,cross_attn,norm,ffn,norm;
+ *                                 detr3d_transformer.py:386-390, deform3d_cross_attn.py:326-339)
+ *                                 and the Linear-LN-ReLU stages of position_encoder
+ *                                 (detr3d_transformer.py:297-304, deform3d_cross_attn.py:112-121)
+ */
+#ifndef GD4D_GLUE_H_
+#define GD4D_GLUE_H_
+
+#include "gd4d_xview.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* y = log(x1 / x2),  xc = clamp(x,0,1), x1 = clamp(xc, eps[, 1]), x2 = clamp(1-xc, eps[, 1]). */
+GD4D_API int gd4d_inverse_sigmoid_fwd(const float* x, float* y, int64_t n, float eps,
+                                      int32_t clamp_max, void* cuda_stream);
+/* gx = gy * [0<=x<=1] * ([xc>=eps]/x1 + [1-xc>=eps]/x2)   (torch clamp passes gradient on ties) */
+GD4D_API int gd4d_inverse_sigmoid_bwd(const float* x, const float* gy, float* gx, int64_t n,
+                                      float eps, int32_t clamp_max, void* cuda_stream);
+
+/* new_ref[r,0:2] = sigmoid(reg[r,0:2] + inverse_sigmoid(ref[r,0:2]))
+ * new_ref[r,2]   = sigmoid(reg[r,4]   + inverse_sigmoid(ref[r,2]))
+ * reg is (rows, reg_stride) with reg_stride >= 5 (the 10-wide box code); ref/new_ref (rows,3). */
+GD4D_API int gd4d_ref_update(const float* reg, int32_t reg_stride, const float* ref, float* new_ref,
+                             int64_t rows, float eps, void* cuda_stream);
+
+/* y = [relu](y + bias) in place: the bias/activation epilogue of a Linear whose GEMM ran
+ * without one (fp32 cuBLAS runs it as a separate kernel, and ReLU as another).
+ * y (rows,C), bias (C), C % 4 == 0, 16-byte aligned. */
+GD4D_API int gd4d_bias_act(float* y, const float* bias, int64_t rows, int32_t C, int32_t relu,
+                           void* cuda_stream);
+
+/* s = x + xbias + r1 + r2 (xbias (C) broadcast over rows; xbias, r1, r2 optional);
+ * y = LayerNorm_C(s) * gamma + beta;  y = max(y,0) if relu.
+ * Writes y (rows,C), mean/rstd (rows) and s (s_out is required whenever s != x).
+ * C must be a multiple of 128 and <= 1024; all row pointers 16-byte aligned. */
+GD4D_API int gd4d_add_layernorm_fwd(const float* x, const float* xbias, const float* r1,
+                                    const float* r2, const float* gamma, const float* beta,
+                                    float* y, float* s_out, float* mean, float* rstd,
+                                    int64_t rows, int32_t C, float eps, int32_t relu,
+                                    void* cuda_stream);
+/* gs = dL/ds (the same gradient flows to x, r1 and r2).  With relu the incoming gradient is
+ * first masked by [y > 0] (recomputed from s, mean, rstd, gamma, beta) and, if g_masked != NULL,
+ * the masked gradient is written out for the deferred gamma/beta reduction. */
+GD4D_API int gd4d_add_layernorm_bwd(const float* gy, const float* s, const float* mean,
+                                    const float* rstd, const float* gamma, const float* beta,
+                                    float* gs, float* g_masked, int64_t rows, int32_t C,
+                                    int32_t relu, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GD4D_GLUE_H_ */

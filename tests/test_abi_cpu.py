@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    src = open(os.path.join(ROOT, "include", "gd4d_xview.h")).read()
+    src = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("gd4d_xview.h", "gd4d_glue.h"))
     return re.findall(r"GD4D_API\s+[\w\s\*]+?\b(gd4d_\w+)\s*\(", src)
 
 
@@ -69,5 +69,15 @@ def test_launch_info_and_status_codes():
     assert lib.gd4d_xview_backward(C.byref(q), None) == -1          # validation precedes any launch
     assert lib.gd4d_pack_nchw(None, None, 0, 0, 1, 1, 1, 1, None) == -1
     assert lib.gd4d_pack_nchw(0x1000, 0x2000, 0, 0, 0, 1, 1, 1, None) == -2
+    # glue entry points validate before launching, too
+    assert lib.gd4d_inverse_sigmoid_fwd(None, None, 1, 1e-5, 0, None) == -1
+    assert lib.gd4d_inverse_sigmoid_bwd(0x1000, 0x1000, 0x1000, 0, 1e-5, 0, None) == -2
+    assert lib.gd4d_ref_update(0x1000, 4, 0x1000, 0x1000, 10, 1e-5, None) == -2      # reg_stride < 5
+    a = 0x1000
+    assert lib.gd4d_add_layernorm_fwd(a, None, None, None, a, a, a, None, a, a, 900, 200, 1e-5, 0, None) == -2
+    assert lib.gd4d_add_layernorm_fwd(a + 4, None, None, None, a, a, a, None, a, a, 900, 256, 1e-5, 0, None) == -4
+    assert lib.gd4d_add_layernorm_fwd(a, a, None, None, a, a, a, None, a, a, 900, 256, 1e-5, 0, None) == -1  # s_out
+    assert lib.gd4d_bias_act(a, a, 900, 10, 1, None) == -2                                      # C % 4
+    assert lib.gd4d_add_layernorm_bwd(a, a, a, a, a, None, a, None, 900, 256, 1, None) == -1   # relu needs beta
     for code in (0, -1, -2, -3, -4, -5, -6, -99):
         assert len(_lib.strerror(code)) > 0

@@ -85,8 +85,11 @@ def test_cuda_graph_step_matches_eager():
         loss.backward()
         opt.step()
         losses.append(float(loss))
-    assert abs(l_g[0] - losses[3]) <= 1e-4 * abs(losses[3])
-    assert abs(l_g[1] - losses[4]) <= 1e-4 * abs(losses[4])
+    # 3-4 Adam steps in, the two runs differ by atomics-order noise amplified by Adam's sign-like
+    # updates (observed up to 3e-4 relative on 1 run in 6); a wrong or missing gradient moves the
+    # loss by far more than 1e-3.
+    assert abs(l_g[0] - losses[3]) <= 1e-3 * abs(losses[3])
+    assert abs(l_g[1] - losses[4]) <= 1e-3 * abs(losses[4])
     # Adam normalises each update to ~lr whatever the gradient's size, so an element whose
     # gradient sits at the fp32-atomics noise floor can move by up to 2*lr per step in either
     # run: bound the drift (5 steps * 2 * lr) and require such elements to be a small minority

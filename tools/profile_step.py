@@ -27,9 +27,12 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
-ev = [e for e in prof.key_averages() if e.device_time_total > 0 or getattr(e, "self_device_time_total", 0) > 0]
-rows = sorted(((e.self_device_time_total / 3.0, e.count / 3, e.key) for e in prof.key_averages() if e.self_device_time_total > 0), reverse=True)
+from torch.autograd import DeviceType
+kern = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA and e.self_device_time_total > 0]
+rows = sorted(((e.self_device_time_total / 3.0, e.count / 3, e.key) for e in kern), reverse=True)
 tot = sum(r[0] for r in rows)
-print(f"total device time per step: {tot/1e3:.3f} ms")
-for t, n, k in rows[:45]:
-    print(f"{t:9.1f} us {100*t/tot:5.1f}% n={n:6.1f} {k[:110]}")
+print(f"kernel time per step: {tot/1e3:.3f} ms in {sum(r[1] for r in rows):.0f} launches")
+ours = sum(r[0] for r in rows if "gd4d::" in r[2])
+print(f"libgd4d_xview.so kernels: {ours/1e3:.3f} ms ({100*ours/tot:.1f}%), {sum(r[1] for r in rows if 'gd4d::' in r[2]):.0f} launches")
+for t, n, k in rows[:70]:
+    print(f"{t:9.1f} us {100*t/tot:5.1f}% n={n:6.1f} {k[:150]}")
