@@ -13,7 +13,7 @@ import threading
 
 from . import _build
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LEVELS = 8
 MODE_A, MODE_C, MODE_V2 = 0, 1, 2
 F32, BF16 = 0, 1
@@ -47,6 +47,7 @@ class XViewParams(C.Structure):
         ("L", C.c_int32), ("P", C.c_int32), ("C", C.c_int32),
         ("wide", C.c_int32),
         ("flags", C.c_uint32),
+        ("gen_stride", C.c_int32),
         ("level_h", C.c_int32 * MAX_LEVELS),
         ("level_w", C.c_int32 * MAX_LEVELS),
         ("pc_lo", C.c_float * 3),

@@ -42,6 +42,11 @@ static int validate(const gd4d_xview_params* p, bool backward, LaunchGeom* g) {
   if (p->mode == GD4D_MODE_C) {
     if (p->offsets == nullptr || p->cam_logits == nullptr) return GD4D_ERR_NULL;
     if (p->L * p->P > kMaxLP) return GD4D_ERR_UNSUPPORTED;
+    if (p->gen_stride < 0 ||
+        (p->gen_stride > 0 && p->gen_stride < p->Hh * p->L * p->P + p->Hh * p->P * 3 + p->N))
+      return GD4D_ERR_DIMS;
+  } else if (p->gen_stride != 0) {
+    return GD4D_ERR_UNSUPPORTED;
   }
   if (p->mode == GD4D_MODE_V2) {
     if (p->offsets == nullptr) return GD4D_ERR_NULL;

@@ -291,7 +291,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
       float dot = s0 * g0 + s1 * g1;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      float* ga = p.grad_attn_logits + (static_cast<size_t>(w.bq) * p.Hh + w.h) * LP;
+      float* ga = p.grad_attn_logits + attn_row_off(p, w);
       if (lane < LP) atomicAdd(ga + lane, s0 * (g0 - dot));
       if (lane + 32 < LP) atomicAdd(ga + lane + 32, s1 * (g1 - dot));
     }
@@ -314,9 +314,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
         atomicAdd(&doff[pi * 3 + 1], dY);
         atomicAdd(&doff[pi * 3 + 2], dZ);
         if (p.grad_cam_logits != nullptr)
-          atomicAdd(p.grad_cam_logits + static_cast<size_t>(w.b) * p.N * p.Q +
-                        static_cast<size_t>(n) * p.Q + w.q,
-                    cd.w * (1.f - cd.w) * cd.cg);
+          atomicAdd(p.grad_cam_logits + cam_off(p, w, n), cd.w * (1.f - cd.w) * cd.cg);
       }
     }
     if (p.grad_ref != nullptr) {
@@ -335,7 +333,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     }
     if (MODE == GD4D_MODE_C && p.grad_offsets != nullptr) {
       __syncwarp();
-      float* go = p.grad_offsets + (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.P * 3;
+      float* go = p.grad_offsets + offsets_row_off(p, w);
       for (int i = lane; i < p.P * 3; i += 32) atomicAdd(go + i, doff[i]);
     }
     __syncwarp();  // per-warp shared-memory state is reused by the next work item

@@ -222,11 +222,31 @@ __device__ __forceinline__ void work_end(const gd4d_xview_params& p, const WorkI
   }
 }
 
+// Mode C generator outputs (attn_logits / offsets / cam_logits and their gradients): dense
+// per-tensor layouts when gen_stride == 0, else column blocks of one row-major
+// (B*Q, gen_stride) matrix (include/gd4d_xview.h).
+__device__ __forceinline__ size_t attn_row_off(const gd4d_xview_params& p, const WarpCtx& w) {
+  const int LP = p.L * p.P;
+  return p.gen_stride > 0 ? static_cast<size_t>(w.bq) * p.gen_stride + w.h * LP
+                          : (static_cast<size_t>(w.bq) * p.Hh + w.h) * LP;
+}
+__device__ __forceinline__ size_t offsets_row_off(const gd4d_xview_params& p, const WarpCtx& w) {
+  return p.gen_stride > 0 ? static_cast<size_t>(w.bq) * p.gen_stride + w.h * p.P * 3
+                          : (static_cast<size_t>(w.bq) * p.Hh + w.h) * p.P * 3;
+}
+// the reference views the (B,Q,N) Linear output as (B,N,Q): weight(n,q) = flat[n*Q + q]
+__device__ __forceinline__ size_t cam_off(const gd4d_xview_params& p, const WarpCtx& w, int n) {
+  const size_t e = static_cast<size_t>(n) * p.Q + w.q;
+  if (p.gen_stride > 0)
+    return (static_cast<size_t>(w.b) * p.Q + e / p.N) * p.gen_stride + e % p.N;
+  return static_cast<size_t>(w.b) * p.N * p.Q + e;
+}
+
 // softmax over the head's L*P (<= 64) logits into sw[0..64) (zeros past L*P)
 __device__ __forceinline__ void head_softmax(const gd4d_xview_params& p, const WarpCtx& w, float* sw) {
   const int LP = p.L * p.P;
   const int lane = w.lane;
-  const float* a = p.attn_logits + (static_cast<size_t>(w.bq) * p.Hh + w.h) * LP;
+  const float* a = p.attn_logits + attn_row_off(p, w);
   const float x0 = lane < LP ? __ldg(a + lane) : -INFINITY;
   const float x1 = lane + 32 < LP ? __ldg(a + lane + 32) : -INFINITY;
   float m = fmaxf(x0, x1);
@@ -262,7 +282,7 @@ __device__ __forceinline__ int build_candidates(const gd4d_xview_params& p, cons
       pi = c - n * PP;
       float X = w.X0, Y = w.Y0, Z = w.Z0;
       if (MODE == GD4D_MODE_C) {
-        const float* o = p.offsets + ((static_cast<size_t>(w.bq) * p.Hh + w.h) * p.P + pi) * 3;
+        const float* o = p.offsets + offsets_row_off(p, w) + pi * 3;
         X = __fadd_rn(X, __ldg(o + 0));
         Y = __fadd_rn(Y, __ldg(o + 1));
         Z = __fadd_rn(Z, __ldg(o + 2));
@@ -277,8 +297,7 @@ __device__ __forceinline__ int build_candidates(const gd4d_xview_params& p, cons
           p.mask[static_cast<size_t>(w.bq) * p.N + n] = valid;
       }
       if (valid && MODE == GD4D_MODE_C)  // reference views (B,Q,N) memory as (B,N,Q): flat[n*Q+q]
-        wc = sigmoidf_(__ldg(p.cam_logits + static_cast<size_t>(w.b) * p.N * p.Q +
-                             static_cast<size_t>(n) * p.Q + w.q));
+        wc = sigmoidf_(__ldg(p.cam_logits + cam_off(p, w, n)));
     }
     const unsigned bal = __ballot_sync(0xffffffffu, valid);
     if (valid) cands[nvalid + __popc(bal & ((1u << w.lane) - 1u))] = CandT::make(pr, n, pi, wc);

@@ -160,6 +160,75 @@ class _LinearReluFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+_PAD = {}
+
+
+def _pad_zeros(like: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    key = (like.device, like.dtype, rows, cols)
+    z = _PAD.get(key)
+    if z is None:
+        with torch.no_grad():
+            z = _PAD[key] = torch.zeros(rows, cols, device=like.device, dtype=like.dtype)
+    return z
+
+
+class _CatLinearFn(torch.autograd.Function):
+    """Several Linears on the SAME input as ONE GEMM over their concatenated weights:
+    y (.., width) = x @ cat(W_i)^T + cat(b_i), columns padded with zeros to ``width``.
+    Backward: one dX GEMM; each Linear's weight/bias gradient is its column block of G^T X
+    (deferred and batched under DeferredWgrad).  inputs: x, width, *(w0, b0, w1, b1, ...)."""
+
+    @staticmethod
+    def forward(ctx, x, width: int, *wb):
+        from . import fused
+        ws, bs = wb[0::2], wb[1::2]
+        n = sum(int(w.shape[0]) for w in ws)
+        K = x.shape[-1]
+        pad = width - n
+        x2 = x.reshape(-1, K)
+        wc = torch.cat(list(ws) + ([_pad_zeros(x, pad, K)] if pad else []))
+        bc = torch.cat(list(bs) + ([_pad_zeros(x, 1, pad).view(-1)] if pad else []))
+        y = x.new_empty(*x.shape[:-1], width)
+        torch.mm(x2, wc.t(), out=y.view(-1, width))
+        fused.bias_act_(y, bc, relu=False)
+        ctx.save_for_backward(x2, wc)
+        ctx.xshape = x.shape
+        ctx.params = [(w, b) for w, b in zip(ws, bs)]
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, wc = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        dx = (g2 @ wc).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        q = DeferredWgrad._active
+        grads, c0 = [], 0
+        dwc = dbc = None
+        for i, (w, b) in enumerate(ctx.params):
+            c1 = c0 + int(w.shape[0])
+            need = ctx.needs_input_grad[2 + 2 * i]
+            if need and q is not None and w.is_leaf:
+                q.items.append((w, b, 0, int(w.shape[0]), g2[:, c0:c1], x2))
+                grads += [None, None]
+            elif need:
+                if dwc is None:
+                    dwc = g2.t() @ x2
+                    dbc = (g2.new_ones(1, g2.shape[0]) @ g2).view(-1)
+                grads += [dwc[c0:c1], dbc[c0:c1]]
+            else:
+                grads += [None, None]
+            c0 = c1
+        return (dx, None, *grads)
+
+
+def cat_linear(x: torch.Tensor, lins, width: int) -> torch.Tensor:
+    """(.., width) = [lin_0(x) | lin_1(x) | ... | 0-padding], one GEMM (CUDA fp32 only)."""
+    wb = []
+    for lin in lins:
+        wb += [lin.weight, lin.bias]
+    return _CatLinearFn.apply(x, int(width), *wb)
+
+
 class _FastLayerNormFn(torch.autograd.Function):
     """LayerNorm whose gamma/beta gradients (a 12 us column reduction each, 30 per step) can be
     deferred to one batched reduction (DeferredWgrad); dX is computed immediately."""

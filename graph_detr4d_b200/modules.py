@@ -48,10 +48,13 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import fused, ops
-from .glue import can_defer_bias, fast_layer_norm, fast_linear
+from .glue import can_defer_bias, cat_linear, fast_layer_norm, fast_linear
 from .ops import MODE_A, MODE_C, MODE_V2, PackedFeatures, XViewConfig
 
+import os as _os
 import sys as _sys
+
+_PACKED_GEN = _os.environ.get("GD4D_PACKED_GEN", "1") != "0"    # A/B switch for measurements
 
 
 def _real_mmcv_available() -> bool:
@@ -555,15 +558,33 @@ class Deform3DCrossAttn(BaseModule):
         if packed.N != self.num_cams or len(packed.levels) != self.num_levels:
             raise ValueError(f"expected {self.num_cams} cams x {self.num_levels} levels, got "
                              f"{packed.N} x {len(packed.levels)}")
-        cam_logits = fast_linear(query, self.cam_attention_weights)    # (B,Q,N); kernel reads it as view(B,N,Q)
-        offsets = fast_linear(query, self.deform_sampling_offsets)     # (B,Q,Hh*P*3)
-        logits = fast_linear(query, self.attention_weights)            # (B,Q,Hh*L*P)
         img_h, img_w = _img_hw(img_metas)
         l2i = _L2I_CACHE.get(img_metas, query.device)
+        # The three generator Linears read the same query: on the CUDA fp32 path they are ONE GEMM over
+        # the concatenated weights, and the kernels read / write their column blocks in place (gen_stride).
+        packed_gen = fused.ENABLED and _PACKED_GEN and can_defer_bias(query, self.attention_weights)
+        if packed_gen:
+            n_attn = self.num_heads * self.num_levels * self.num_points
+            n_off = self.num_heads * self.num_points * 3
+            layout = ops.GenLayout(cam=n_attn + n_off, offsets=n_attn, attn=0,
+                                   width=(n_attn + n_off + self.num_cams + 3) // 4 * 4)
+            gen = cat_linear(query, (self.attention_weights, self.deform_sampling_offsets,
+                                     self.cam_attention_weights), layout.width)          # (B,Q,width)
+
+            def sample(cfg, values=None):
+                return ops.xview_attention_gen(cfg, packed, reference_points, gen, layout, l2i, values=values)
+        else:
+            cam_logits = fast_linear(query, self.cam_attention_weights)    # (B,Q,N); kernel reads it as view(B,N,Q)
+            offsets = fast_linear(query, self.deform_sampling_offsets)     # (B,Q,Hh*P*3)
+            logits = fast_linear(query, self.attention_weights)            # (B,Q,Hh*L*P)
+
+            def sample(cfg, values=None):
+                return ops.xview_attention(cfg, packed, reference_points, logits, offsets, cam_logits, l2i,
+                                           values=values)
         if self._use_wide(packed):
             cfg = XViewConfig(MODE_C, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w,
                               wide=True)
-            agg, wsum = ops.xview_attention(cfg, packed, reference_points, logits, offsets, cam_logits, l2i)
+            agg, wsum = sample(cfg)
             Hh, Ch = self.num_heads, self.embed_dims // self.num_heads
             wv = self.value_proj.weight.view(Hh, Ch, self.embed_dims)       # out channel = h*Ch + c
             # agg is head-major (B,Hh,Q,C): one strided-batched GEMM, no transpose copy of the 7 MB aggregate
@@ -577,8 +598,7 @@ class Deform3DCrossAttn(BaseModule):
             out = out.view(Bq, Hh, Qn, Ch).permute(0, 2, 1, 3).flatten(2)       # (B,Q,C)
         else:
             cfg = XViewConfig(MODE_C, self.num_heads, self.num_points, tuple(self.pc_range), img_h, img_w)
-            out = ops.xview_attention(cfg, packed, reference_points, logits, offsets, cam_logits, l2i,
-                                      values=self.project_values(packed))  # (B,Q,C)
+            out = sample(cfg, self.project_values(packed))                 # (B,Q,C)
         out, pending = _output_proj(out, self.output_proj, self.dropout, defer_bias)
         out = out.permute(1, 0, 2)
         r3d = reference_points

@@ -16,8 +16,8 @@ import torch
 from . import _lib
 from ._lib import BF16, F32, MODE_A, MODE_C, MODE_V2, XViewParams
 
-__all__ = ["XViewConfig", "pack_features", "PackedFeatures", "xview_forward", "xview_backward",
-           "xview_attention", "lidar2img_to_tensor", "prepare_forward", "prepare_backward",
+__all__ = ["XViewConfig", "GenLayout", "pack_features", "PackedFeatures", "xview_forward", "xview_backward",
+           "xview_attention", "xview_attention_gen", "xview_forward_gen", "xview_backward_gen", "lidar2img_to_tensor", "prepare_forward", "prepare_backward",
            "launch_count", "MODE_A", "MODE_C", "MODE_V2"]
 
 DYNAMIC_SCHEDULE = True   # persistent grid + work counter (False: one warp per item, static)
@@ -234,8 +234,20 @@ class XViewConfig:
     wide: bool = False          # mode C: gather-then-project (include/gd4d_xview.h)
 
 
+@dataclass(frozen=True)
+class GenLayout:
+    """Column offsets (in floats) of the three generator blocks inside one packed row-major
+    (B*Q, width) matrix -- the output of ONE GEMM over the concatenated weights of
+    cam_attention_weights / deform_sampling_offsets / attention_weights (gen_stride in
+    include/gd4d_xview.h)."""
+    cam: int
+    offsets: int
+    attn: int
+    width: int
+
+
 def _fill_params(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
-                 offsets, cam_logits, lidar2img) -> XViewParams:
+                 offsets, cam_logits, lidar2img, gen=None, layout: Optional[GenLayout] = None) -> XViewParams:
     L = len(values)
     if L > _lib.MAX_LEVELS:
         raise ValueError(f"at most {_lib.MAX_LEVELS} feature levels")
@@ -262,9 +274,14 @@ def _fill_params(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: in
     p.img_h, p.img_w = float(cfg.img_h), float(cfg.img_w)
     p.ref = ref.data_ptr()
     p.lidar2img = lidar2img.data_ptr()
-    p.attn_logits = attn_logits.data_ptr()
-    p.offsets = offsets.data_ptr() if offsets is not None else None
-    p.cam_logits = cam_logits.data_ptr() if cam_logits is not None else None
+    if gen is not None:
+        base = gen.data_ptr()
+        p.attn_logits, p.offsets, p.cam_logits = base + 4 * layout.attn, base + 4 * layout.offsets, base + 4 * layout.cam
+        p.gen_stride = layout.width
+    else:
+        p.attn_logits = attn_logits.data_ptr()
+        p.offsets = offsets.data_ptr() if offsets is not None else None
+        p.cam_logits = cam_logits.data_ptr() if cam_logits is not None else None
     if DYNAMIC_SCHEDULE and cfg.mode == MODE_C:
         # mode A launches are ~10 us of work: the per-item claim costs more than the tail it removes
         p.sched = _sched_ptr(ref.device)
@@ -432,6 +449,74 @@ def prepare_backward(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, l
                            grad_wsum, list(grad_values), smalls))
 
 
+def _check_gen(cfg, B, N, L, ref, gen, layout: GenLayout, lidar2img):
+    Q = ref.shape[1]
+    if cfg.mode != MODE_C:
+        raise ValueError("the packed generator layout is a mode C feature")
+    if tuple(ref.shape) != (B, Q, 3) or tuple(lidar2img.shape) != (B, N, 4, 4):
+        raise ValueError("bad reference_points / lidar2img shape")
+    if tuple(gen.shape) != (B, Q, layout.width):
+        raise ValueError(f"packed generator output must be (B,Q,{layout.width}), got {tuple(gen.shape)}")
+    blocks = sorted([(layout.cam, N), (layout.offsets, cfg.num_heads * cfg.num_points * 3),
+                     (layout.attn, cfg.num_heads * L * cfg.num_points)])
+    end = 0
+    for start, width in blocks:
+        if start < end:
+            raise ValueError("generator blocks overlap")
+        end = start + width
+    if end > layout.width:
+        raise ValueError("generator blocks exceed the packed width")
+
+
+def xview_forward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layout: GenLayout, lidar2img):
+    """Mode C forward reading logits / offsets / camera logits as column blocks of ``gen``."""
+    for v in values:
+        _require_cuda(v, "value")
+    ref, gen, lidar2img = _f32c(ref, "reference_points"), _f32c(gen, "gen"), _f32c(lidar2img, "lidar2img")
+    L, Cc = len(values), int(values[0].shape[-1])
+    _check_gen(cfg, B, N, L, ref, gen, layout, lidar2img)
+    p = _fill_params(cfg, values, B, N, ref, None, None, None, lidar2img, gen=gen, layout=layout)
+    Q = int(ref.shape[1])
+    out = torch.empty(_out_shape(cfg, B, Q, Cc), device=ref.device, dtype=torch.float32)
+    p.out = out.data_ptr()
+    wsum = None
+    if cfg.wide:
+        wsum = torch.empty((B, cfg.num_heads, Q), device=ref.device, dtype=torch.float32)
+        p.wsum = wsum.data_ptr()
+    _lib.check(_lib.load().gd4d_xview_forward(C.byref(p), _stream_ptr(ref.device)), "gd4d_xview_forward")
+    _count()
+    return (out, wsum) if cfg.wide else out
+
+
+def xview_backward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layout: GenLayout, lidar2img,
+                       grad_out, grad_values, need_ref: bool = True, grad_wsum=None):
+    """Backward of ``xview_forward_gen``: returns (grad_gen (B,Q,width), grad_ref|None), one
+    zero-filled allocation for both."""
+    grad_out = _f32c(grad_out, "grad_out")
+    p = _fill_params(cfg, values, B, N, ref, None, None, None, lidar2img, gen=gen, layout=layout)
+    p.grad_out = grad_out.data_ptr()
+    if grad_wsum is not None:
+        grad_wsum = _f32c(grad_wsum, "grad_wsum")
+        p.grad_wsum = grad_wsum.data_ptr()
+    if grad_values is not None:
+        for l, gvl in enumerate(grad_values):
+            if gvl.dtype != torch.float32 or gvl.shape != values[l].shape or not gvl.is_contiguous():
+                raise ValueError("grad_values must be fp32, contiguous, shaped like the value levels")
+            p.grad_value[l] = gvl.data_ptr()
+    n_gen, n_ref = gen.numel(), (ref.numel() if need_ref else 0)
+    small = torch.zeros(n_gen + n_ref, device=ref.device, dtype=torch.float32)
+    g_gen = small[:n_gen].view(gen.shape)
+    g_ref = small[n_gen:].view(ref.shape) if need_ref else None
+    base = g_gen.data_ptr()
+    p.grad_attn_logits = base + 4 * layout.attn
+    p.grad_offsets = base + 4 * layout.offsets
+    p.grad_cam_logits = base + 4 * layout.cam
+    p.grad_ref = g_ref.data_ptr() if g_ref is not None else None
+    _lib.check(_lib.load().gd4d_xview_backward(C.byref(p), _stream_ptr(ref.device)), "gd4d_xview_backward")
+    _count()
+    return g_gen, g_ref
+
+
 # --------------------------------------------------------------------------------------
 # autograd
 # --------------------------------------------------------------------------------------
@@ -486,6 +571,51 @@ class _XViewFn(torch.autograd.Function):
         return (None, None, None, g_ref if nd[_I_REF] else None, g_attn if nd[_I_ATTN] else None,
                 g_off if (ctx.has_off and nd[_I_OFF]) else None,
                 g_cam if (ctx.has_cam and nd[_I_CAM]) else None, None, g_token, None, *gv)
+
+
+class _XViewGenFn(torch.autograd.Function):
+    """inputs: cfg, B, N, ref, gen, layout, lidar2img, token, sink, *values  (mode C, packed
+    generator output; same token/sink contract as _XViewFn)."""
+
+    @staticmethod
+    def forward(ctx, cfg: XViewConfig, B: int, N: int, ref, gen, layout: GenLayout, lidar2img,
+                token, sink, *values):
+        ref_c, gen_c, l2i_c = _f32c(ref, "reference_points"), _f32c(gen, "gen"), _f32c(lidar2img, "lidar2img")
+        res = xview_forward_gen(cfg, values, B, N, ref_c, gen_c, layout, l2i_c)
+        ctx.cfg, ctx.B, ctx.N, ctx.sink, ctx.layout = cfg, B, N, sink, layout
+        ctx.save_for_backward(ref_c, gen_c, l2i_c, *values)
+        return res
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_wsum=None):
+        ref, gen, l2i, *values = ctx.saved_tensors
+        nd = ctx.needs_input_grad
+        use_sink = ctx.sink is not None and nd[7]
+        need_values = any(nd[9:])
+        grad_values = None
+        if use_sink:
+            grad_values = ctx.sink.get()
+        elif need_values:
+            grad_values = [torch.zeros(v.shape, device=v.device, dtype=torch.float32) for v in values]
+        g_gen, g_ref = xview_backward_gen(ctx.cfg, values, ctx.B, ctx.N, ref, gen, ctx.layout, l2i, grad_out,
+                                          grad_values, need_ref=nd[3],
+                                          grad_wsum=grad_wsum if ctx.cfg.wide else None)
+        gv = [None] * len(values)
+        if need_values and not use_sink:
+            gv = [g if g.dtype == v.dtype else g.to(v.dtype) for g, v in zip(grad_values, values)]
+        g_token = grad_out.new_zeros(()) if use_sink else None
+        return (None, None, None, g_ref if nd[3] else None, g_gen if nd[4] else None, None, None, g_token,
+                None, *gv)
+
+
+def xview_attention_gen(cfg: XViewConfig, packed: PackedFeatures, ref, gen, layout: GenLayout, lidar2img,
+                        values: Optional[Sequence[torch.Tensor]] = None):
+    """``xview_attention`` for mode C with the three generator outputs packed in ONE
+    (B,Q,layout.width) tensor (no split copies forward, no concatenation backward)."""
+    if values is not None:
+        return _XViewGenFn.apply(cfg, packed.B, packed.N, ref, gen, layout, lidar2img, None, None, *values)
+    return _XViewGenFn.apply(cfg, packed.B, packed.N, ref, gen, layout, lidar2img, packed.token, packed.sink,
+                             *packed.levels)
 
 
 def xview_attention(cfg: XViewConfig, packed: PackedFeatures, ref, attn_logits, offsets=None,

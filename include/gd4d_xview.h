@@ -40,7 +40,7 @@ extern "C" {
 #define GD4D_API
 #endif
 
-#define GD4D_ABI_VERSION 4
+#define GD4D_ABI_VERSION 5
 #define GD4D_MAX_LEVELS 8
 
 typedef enum gd4d_status {
@@ -112,6 +112,14 @@ typedef struct gd4d_xview_params {
   int32_t B, Q, N, Hh, L, P, C;
   int32_t wide;                 /* mode C only: 0 = head slices of projected value, 1 = see above */
   uint32_t flags;               /* GD4D_FLAG_* */
+  int32_t gen_stride;           /* mode C only.  0: attn_logits / offsets / cam_logits (and their
+                                   gradients) are the dense tensors described above.  > 0: they are
+                                   COLUMN BLOCKS of one row-major (B*Q, gen_stride) fp32 matrix -- the
+                                   output of ONE GEMM over the three generator Linears' concatenated
+                                   weights: each pointer addresses its block's first column in row 0,
+                                   row b*Q+q holds query q's Hh*L*P logits, Hh*P*3 offsets and N camera
+                                   logits; the camera logit of (n,q) is element e = n*Q+q of the (Q,N)
+                                   block, i.e. row e/N, column e%N (the reference's view quirk). */
   int32_t level_h[GD4D_MAX_LEVELS];
   int32_t level_w[GD4D_MAX_LEVELS];
   float pc_lo[3];               /* pc_range[0:3]                              */

@@ -128,6 +128,38 @@ def test_linear_relu_and_deferred_bias_match_torch():
     assert _rel(ling.weight.grad, lin.weight.grad) <= 5e-5 and _rel(ling.bias.grad, lin.bias.grad) <= 5e-5
 
 
+def test_cat_linear_is_three_linears():
+    """One GEMM over concatenated weights == the three generator Linears, gradients included
+    (immediate and deferred), with zero padding columns that receive no gradient."""
+    from graph_detr4d_b200 import glue
+    g = torch.Generator().manual_seed(21)
+    lins = [torch.nn.Linear(256, n) for n in (128, 96, 6)]
+    x = torch.randn(1, 900, 256, generator=g)
+    gy = torch.randn(1, 900, 232, generator=g)
+    xo = x.clone().requires_grad_(True)
+    yo = torch.cat([l(xo) for l in lins], -1)
+    yo.backward(gy[..., :230])
+    lg = [torch.nn.Linear(256, n).cuda() for n in (128, 96, 6)]
+    for a_, b_ in zip(lg, lins):
+        a_.load_state_dict(b_.state_dict())
+    for deferred in (False, True):
+        for l in lg:
+            l.zero_grad(set_to_none=True)
+        xg = x.cuda().requires_grad_(True)
+        y = glue.cat_linear(xg, lg, 232)
+        assert tuple(y.shape) == (1, 900, 232) and float(y[..., 230:].abs().max()) == 0.0
+        assert _rel(y[..., :230].detach(), yo.detach()) <= TOL
+        if deferred:
+            with DeferredWgrad() as wq:
+                y.backward(gy.cuda())
+                wq.flush()
+        else:
+            y.backward(gy.cuda())
+        assert _rel(xg.grad, xo.grad) <= 5e-5
+        for a_, b_ in zip(lg, lins):
+            assert _rel(a_.weight.grad, b_.weight.grad) <= 5e-5 and _rel(a_.bias.grad, b_.bias.grad) <= 5e-5
+
+
 def test_position_encoder_uses_fused_stages_and_matches_torch():
     seq = modules._position_encoder(3, 256)
     g = torch.Generator().manual_seed(5)
