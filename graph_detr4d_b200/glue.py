@@ -318,6 +318,53 @@ class _ScaledBmmNT(torch.autograd.Function):
         return dq, dk, None
 
 
+class _AttnCoreFn(torch.autograd.Function):
+    """softmax(alpha * q k^T) v for the packed projections qk (L,B,2E) and v (L,B,E), heads split
+    as nn.MultiheadAttention does.  Every GEMM reads / writes its operands IN PLACE as strided
+    batches (the per-head views of the packed buffers), forward and backward: no slice, transpose
+    or concatenation copies, no zero fills (stock autograd: ~9 extra launches per layer).
+    Batch 1 only (one scene per GPU): with B > 1 the (B,H) axes of the packed buffer do not merge
+    into one batch stride and the caller uses the generic path."""
+
+    @staticmethod
+    def forward(ctx, qk, v, H: int, alpha: float):
+        L, B, E2 = qk.shape
+        E = E2 // 2
+        d = E // H
+        q = qk[..., :E].reshape(L, B * H, d).transpose(0, 1)              # (B*H,L,d) views
+        k = qk[..., E:].reshape(L, B * H, d).transpose(0, 1)
+        vv = v.reshape(L, B * H, d).transpose(0, 1)
+        attn = torch.baddbmm(_zero(qk), q, k.transpose(1, 2), beta=0.0, alpha=alpha)
+        attn = torch._softmax(attn, -1, False)
+        out = qk.new_empty(L, B, E)
+        torch.bmm(attn, vv, out=out.view(L, B * H, d).transpose(0, 1))
+        ctx.save_for_backward(qk, v, attn)
+        ctx.H, ctx.alpha = H, alpha
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qk, v, attn = ctx.saved_tensors
+        L, B, E2 = qk.shape
+        E = E2 // 2
+        H, d = ctx.H, E // ctx.H
+        g = g.contiguous()
+        gg = g.view(L, B * H, d).transpose(0, 1)                            # (B*H,L,d)
+        q = qk[..., :E].reshape(L, B * H, d).transpose(0, 1)
+        k = qk[..., E:].reshape(L, B * H, d).transpose(0, 1)
+        vv = v.reshape(L, B * H, d).transpose(0, 1)
+        dv = torch.empty_like(v)
+        torch.bmm(attn.transpose(1, 2), gg, out=dv.view(L, B * H, d).transpose(0, 1))
+        ds = torch._softmax_backward_data(torch.bmm(gg, vv.transpose(1, 2)), attn, -1, attn.dtype)
+        dqk = torch.empty_like(qk)
+        z = _zero(qk)
+        torch.baddbmm(z, ds, k, beta=0.0, alpha=ctx.alpha,
+                      out=dqk[..., :E].view(L, B * H, d).transpose(0, 1))
+        torch.baddbmm(z, ds.transpose(1, 2), q, beta=0.0, alpha=ctx.alpha,
+                      out=dqk[..., E:].view(L, B * H, d).transpose(0, 1))
+        return dqk, dv, None, None
+
+
 def self_attention(query, query_pos, mha: torch.nn.MultiheadAttention, out_bias: bool = True):
     """nn.MultiheadAttention(q=k=query+pos, v=query), batch_first=False, eval/dropout-free
     math: explicit bmm + softmax (faster than the flash/mem-efficient kernels at L=900,
@@ -330,12 +377,14 @@ def self_attention(query, query_pos, mha: torch.nn.MultiheadAttention, out_bias:
     own = w.requires_grad
     qk = _FastLinearFn.apply(qk_in, w[:2 * E], b[:2 * E], (w, b, 0, 2 * E) if own else None, True)  # (L,B,2E)
     v = _FastLinearFn.apply(query, w[2 * E:], b[2 * E:], (w, b, 2 * E, 3 * E) if own else None, True)  # (L,B,E)
+    if B == 1 and not (mha.dropout > 0 and mha.training) and qk.dtype == torch.float32:
+        out = _AttnCoreFn.apply(qk, v, H, 1.0 / math.sqrt(d))             # (L,B,E)
+        return fast_linear(out, mha.out_proj, add_bias=out_bias)
     q, k = qk[..., :E], qk[..., E:]
     q = q.reshape(L, B * H, d).transpose(0, 1)                          # (B*H,L,d)
     k = k.reshape(L, B * H, d).transpose(0, 1)
     v = v.reshape(L, B * H, d).transpose(0, 1)
     attn = _ScaledBmmNT.apply(q, k, 1.0 / math.sqrt(d)).softmax(-1)
-    if mha.dropout > 0 and mha.training:
-        attn = torch.nn.functional.dropout(attn, mha.dropout)
+    attn = torch.nn.functional.dropout(attn, mha.dropout)
     out = torch.bmm(attn, v).transpose(0, 1).reshape(L, B, E)
     return fast_linear(out, mha.out_proj, add_bias=out_bias)
