@@ -339,7 +339,7 @@ def main():
                     ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype=dtype, data="synthetic",
                     config=dict(workload=workload_name(T, dtype), layers=LAYERS, queries=Q, cams=N,
-                                points=POINTS, heads=HEADS, per_gpu_batch=1, optimizer="AdamW(fused, capturable)",
+                                points=POINTS, heads=HEADS, per_gpu_batch=1, optimizer="AdamW (one-launch gd4d_adamw_multi, torch.optim.AdamW arithmetic, device step counter)",
                                 value_proj="fused: gather-then-project (no dense per-pixel GEMM)",
                                 execution="CUDA graphs (fwd+bwd graph, NCCL all-reduce of flat grads if N>1, optimizer graph)",
                                 features="NCHW fp32 in, packed channel-last once per step inside the step",

@@ -34,6 +34,8 @@ EXPORTS = (
     "gd4d_bias_act",
     "gd4d_add_layernorm_fwd",
     "gd4d_add_layernorm_bwd",
+    "gd4d_adamw_chunk",
+    "gd4d_adamw_multi",
 )
 
 
@@ -124,7 +126,9 @@ def load(build_if_missing: bool = True):
                 ("gd4d_ref_update", [vp, i32, vp, vp, i64, f32, vp]),
                 ("gd4d_bias_act", [vp, vp, i64, i32, i32, vp]),
                 ("gd4d_add_layernorm_fwd", [vp] * 10 + [i64, i32, f32, i32, vp]),
-                ("gd4d_add_layernorm_bwd", [vp] * 8 + [i64, i32, i32, vp])):
+                ("gd4d_add_layernorm_bwd", [vp] * 8 + [i64, i32, i32, vp]),
+                ("gd4d_adamw_chunk", []),
+                ("gd4d_adamw_multi", [vp, vp, i32, vp, f32, f32, f32, f32, f32, vp])):
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = C.c_int, args
         lib.gd4d_params_size.restype = C.c_int

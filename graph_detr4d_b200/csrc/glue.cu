@@ -300,3 +300,79 @@ int gd4d_add_layernorm_bwd(const float* gy, const float* s, const float* mean, c
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// AdamW over MANY small tensors in ONE launch (include/gd4d_glue.h: gd4d_adamw_multi).
+// torch's fused AdamW walks 65536-element chunks, one CTA each: the decoder's ~7 M parameters in
+// ~200 tensors become ~150 CTAs spread over 6 launches (39 us each, r1).  Here a CTA owns a
+// 4096-element chunk (block map built once on the host), so the same update is ~2000 CTAs in a
+// single launch, HBM-bound (28 B per element).
+// Math = torch.optim.AdamW(fused=True): decoupled weight decay, lerp for exp_avg, bias
+// corrections from the DEVICE step counter (capturable), evaluated in double like torch.
+// ---------------------------------------------------------------------------------------
+namespace gd4d {
+constexpr int kAdamChunk = 4096;
+
+__global__ void __launch_bounds__(256)
+adamw_multi_kernel(const gd4d_adamw_tensor* __restrict__ table, const int2* __restrict__ block_map,
+                   const float* __restrict__ step_ptr, float lr, float beta1, float beta2, float eps,
+                   float weight_decay) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double step = static_cast<double>(*step_ptr);
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+    s_step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+    s_bc2_sqrt = static_cast<float>(sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const int2 bm = block_map[blockIdx.x];
+  const gd4d_adamw_tensor t = table[bm.x];
+  const int64_t start = static_cast<int64_t>(bm.y) * kAdamChunk;
+  const int64_t end = min(start + kAdamChunk, t.n);
+  const float decay = 1.f - lr * weight_decay;
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
+                     reinterpret_cast<uintptr_t>(t.m) | reinterpret_cast<uintptr_t>(t.v)) & 15u) == 0;
+  auto upd = [&](float& p, float g, float& m, float& v) {
+    p *= decay;
+    m = m + omb1 * (g - m);                      // lerp(m, g, 1 - beta1)
+    v = beta2 * v + omb2 * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p -= step_size * m / denom;
+  };
+  if (vec) {
+    for (int64_t i = start + threadIdx.x * 4; i < end; i += 256 * 4) {
+      if (i + 4 <= end) {
+        float4 p = *reinterpret_cast<float4*>(t.p + i);
+        const float4 g = *reinterpret_cast<const float4*>(t.g + i);
+        float4 m = *reinterpret_cast<float4*>(t.m + i);
+        float4 v = *reinterpret_cast<float4*>(t.v + i);
+        upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+        *reinterpret_cast<float4*>(t.p + i) = p;
+        *reinterpret_cast<float4*>(t.m + i) = m;
+        *reinterpret_cast<float4*>(t.v + i) = v;
+      } else {
+        for (int64_t j = i; j < end; ++j) upd(t.p[j], t.g[j], t.m[j], t.v[j]);
+      }
+    }
+  } else {
+    for (int64_t i = start + threadIdx.x; i < end; i += 256) upd(t.p[i], t.g[i], t.m[i], t.v[i]);
+  }
+}
+}  // namespace gd4d
+
+extern "C" int gd4d_adamw_chunk(void) { return gd4d::kAdamChunk; }
+
+extern "C" int gd4d_adamw_multi(const gd4d_adamw_tensor* table_dev, const int32_t* block_map_dev,
+                                int32_t n_blocks, const float* step_dev, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, void* cuda_stream) {
+  if (table_dev == nullptr || block_map_dev == nullptr || step_dev == nullptr) return GD4D_ERR_NULL;
+  if (n_blocks <= 0) return GD4D_ERR_DIMS;
+  gd4d::adamw_multi_kernel<<<static_cast<unsigned>(n_blocks), 256, 0,
+                             static_cast<cudaStream_t>(cuda_stream)>>>(
+      table_dev, reinterpret_cast<const int2*>(block_map_dev), step_dev, lr, beta1, beta2, eps,
+      weight_decay);
+  return gd4d::launched();
+}

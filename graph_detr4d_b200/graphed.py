@@ -17,6 +17,7 @@ eager, stream-ordered call between the two graphs.)
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence
 
 import torch
@@ -24,6 +25,9 @@ import torch.distributed as dist
 
 from . import modules
 from .glue import DeferredWgrad
+from .optim import MultiTensorAdamW
+
+MULTI_TENSOR_ADAMW = os.environ.get("GD4D_MULTI_ADAMW", "1") != "0"      # A/B switch for measurements
 
 
 class GraphedTrainStep:
@@ -50,7 +54,9 @@ class GraphedTrainStep:
             for p in params:
                 self.flat_views.append(self.flat_grad[o:o + p.numel()].view_as(p))
                 o += p.numel()
-        self.opt = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=True, capturable=True)
+        # one-launch AdamW over all parameter tensors (optim.py); torch.optim.AdamW arithmetic
+        self.opt = (MultiTensorAdamW(params, lr=lr, weight_decay=weight_decay) if MULTI_TENSOR_ADAMW else
+                    torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=True, capturable=True))
         self.static_feats: List[torch.Tensor] = [
             f.detach().clone().requires_grad_(feats_require_grad) for f in example_feats]
         self.img_metas = img_metas
@@ -87,6 +93,8 @@ class GraphedTrainStep:
         self.graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_fb):
             self.static_loss = fwd_bwd()
+        if MULTI_TENSOR_ADAMW:
+            self.opt.prepare()                             # pointer table of the CAPTURED gradient tensors
         self.graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_opt):
             self.opt.step()

@@ -67,6 +67,27 @@ GD4D_API int gd4d_add_layernorm_bwd(const float* gy, const float* s, const float
                                     float* gs, float* g_masked, int64_t rows, int32_t C,
                                     int32_t relu, void* cuda_stream);
 
+/* AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected, step counter on
+ * the device so the launch is CUDA-graph capturable) over MANY tensors in ONE launch.
+ *   table_dev      device array of per-tensor records (all fp32, n elements each)
+ *   block_map_dev  device array of n_blocks (tensor index, chunk index) int32 pairs: CTA b updates
+ *                  elements [chunk*gd4d_adamw_chunk(), +gd4d_adamw_chunk()) of tensor table[idx]
+ *   step_dev       device float: the step count AFTER increment (1 on the first update)
+ * Replaces the optimizer step of the reference's training loop (mmcv OptimizerHook ->
+ * torch.optim.AdamW, projects/configs/detr3d/detr3d_res50.py optimizer = dict(type='AdamW', ...)). */
+typedef struct gd4d_adamw_tensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+} gd4d_adamw_tensor;
+
+GD4D_API int gd4d_adamw_chunk(void);
+GD4D_API int gd4d_adamw_multi(const gd4d_adamw_tensor* table_dev, const int32_t* block_map_dev,
+                              int32_t n_blocks, const float* step_dev, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -187,3 +187,28 @@ def test_glue_refuses_cpu_tensors():
         fused.inverse_sigmoid(torch.rand(4, 3))
     with pytest.raises(RuntimeError):
         fused.add_layernorm(torch.randn(4, 256), torch.nn.LayerNorm(256))
+
+
+def test_multi_tensor_adamw_matches_torch_adamw():
+    """One-launch AdamW == torch.optim.AdamW over several steps, odd sizes and grad-less params included."""
+    from graph_detr4d_b200.optim import MultiTensorAdamW
+    g = torch.Generator().manual_seed(31)
+    shapes = [(256, 256), (512,), (3, 256), (10,), (4097,), (1,), (900, 3), (7, 5, 3)]
+    base = [torch.randn(s, generator=g) for s in shapes]
+    pa = [torch.nn.Parameter(t.clone().cuda()) for t in base]
+    pb = [torch.nn.Parameter(t.clone().cuda()) for t in base]
+    skip = 3                                                              # never gets a gradient
+    oa = torch.optim.AdamW(pa, lr=2e-3, weight_decay=0.05, fused=True)
+    ob = MultiTensorAdamW(pb, lr=2e-3, weight_decay=0.05)
+    for it in range(6):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == skip:
+                continue
+            gr = torch.randn(a.shape, generator=g).cuda() * (10.0 ** (it - 3))
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    for i, (a, b) in enumerate(zip(pa, pb)):
+        assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max()) + 1e-7, i
+    assert torch.equal(pb[skip].detach().cpu(), base[skip])
+    assert float(ob.step_t) == 6.0

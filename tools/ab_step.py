@@ -1,26 +1,44 @@
-"""Resident graphed decoder step time, for A/B of glue changes (dev tool): prints the median of
-5 timings of 50 replays.  GD4D_FUSED_GLUE=0 python tools/ab_step.py  -> eager op chains."""
-import os, sys
+"""Resident graphed decoder step time for A/B of glue changes (dev tool).  All variants are
+captured in ONE process and timed interleaved (round-robin, 8 rounds x 40 replays), because
+process-to-process and minute-to-minute drift on a shared B200 is ~4 % -- larger than most of
+the effects being measured.   VARIANTS=base,no_adamw,no_gen,no_fused python tools/ab_step.py"""
+import os, sys, copy
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from graph_detr4d_b200 import synthetic as syn, fused
+from graph_detr4d_b200 import synthetic as syn, fused, graphed, modules
 from graph_detr4d_b200.graphed import GraphedTrainStep
 
 dev = torch.device("cuda")
 T = int(os.environ.get("T", "1"))
-model = bench.build_model(T, os.environ.get("DTYPE", "f32"), dev)
+names = os.environ.get("VARIANTS", "base,no_adamw,no_gen,no_fused").split(",")
 feats = [f.to(dev) for f in syn.make_feats(1, 6 * T, 256, syn.LEVEL_SHAPES_928x1600)]
 metas = syn.make_img_metas(1, T)
-stepper = GraphedTrainStep(model, lambda f: bench.loss_fn(*(lambda st, _, r: (st, r))(*model(f, metas, 1))), feats, metas)
-for _ in range(10): stepper.step()
+base_model = bench.build_model(T, os.environ.get("DTYPE", "f32"), dev)
+
+
+def build(name):
+    fused.ENABLED = name != "no_fused"
+    modules._PACKED_GEN = name != "no_gen"
+    graphed.MULTI_TENSOR_ADAMW = name != "no_adamw"
+    model = copy.deepcopy(base_model)
+    st = GraphedTrainStep(model, lambda f: bench.loss_fn(*(lambda s, _, r: (s, r))(*model(f, metas, 1))), feats, metas)
+    fused.ENABLED, modules._PACKED_GEN, graphed.MULTI_TENSOR_ADAMW = True, True, True
+    return st
+
+
+steppers = {n: build(n) for n in names}
+for st in steppers.values():
+    for _ in range(10): st.step()
 torch.cuda.synchronize()
-ts = []
-for _ in range(5):
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(50): stepper.step()
-    e.record(); torch.cuda.synchronize()
-    ts.append(s.elapsed_time(e) / 50)
-ts.sort()
-print(f"fused_glue={fused.ENABLED} T={T} ms/step median {ts[2]:.3f} min {ts[0]:.3f} max {ts[-1]:.3f}")
+times = {n: [] for n in names}
+for _ in range(8):
+    for n, st in steppers.items():
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(40): st.step()
+        e.record(); torch.cuda.synchronize()
+        times[n].append(s.elapsed_time(e) / 40)
+for n in names:
+    ts = sorted(times[n])
+    print(f"{n:10s} T={T} ms/step median {ts[len(ts)//2]:.3f} min {ts[0]:.3f} max {ts[-1]:.3f}")

@@ -9,7 +9,8 @@ from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda")
 T = int(os.environ.get("T", "1"))
 model = bench.build_model(T, os.environ.get("DTYPE", "f32"), dev)
-opt = torch.optim.AdamW(model.parameters(), lr=2e-4, fused=True, capturable=True)
+from graph_detr4d_b200.optim import MultiTensorAdamW
+opt = MultiTensorAdamW(list(model.parameters()), lr=2e-4)
 feats = [f.to(dev).requires_grad_(True) for f in syn.make_feats(1, 6 * T, 256, syn.LEVEL_SHAPES_928x1600)]
 metas = syn.make_img_metas(1, T)
 
