@@ -27,6 +27,7 @@ EXPORTS = (
     "gd4d_xview_forward",
     "gd4d_xview_backward",
     "gd4d_pack_nchw",
+    "gd4d_unpack_nhwc",
     # include/gd4d_glue.h
     "gd4d_inverse_sigmoid_fwd",
     "gd4d_inverse_sigmoid_bwd",
@@ -119,14 +120,17 @@ def load(build_if_missing: bool = True):
         lib.gd4d_pack_nchw.restype = C.c_int
         lib.gd4d_pack_nchw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        lib.gd4d_unpack_nhwc.restype = C.c_int
+        lib.gd4d_unpack_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p]
         vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
         for name, args in (
                 ("gd4d_inverse_sigmoid_fwd", [vp, vp, i64, f32, i32, vp]),
                 ("gd4d_inverse_sigmoid_bwd", [vp, vp, vp, i64, f32, i32, vp]),
                 ("gd4d_ref_update", [vp, i32, vp, vp, i64, f32, vp]),
                 ("gd4d_bias_act", [vp, vp, i64, i32, i32, vp]),
-                ("gd4d_add_layernorm_fwd", [vp] * 10 + [i64, i32, f32, i32, vp]),
-                ("gd4d_add_layernorm_bwd", [vp] * 8 + [i64, i32, i32, vp]),
+                ("gd4d_add_layernorm_fwd", [vp] * 12 + [i64, i32, f32, i32, vp]),
+                ("gd4d_add_layernorm_bwd", [vp] * 9 + [i64, i32, i32, vp]),
                 ("gd4d_adamw_chunk", []),
                 ("gd4d_adamw_multi", [vp, vp, i32, vp, f32, f32, f32, f32, f32, vp])):
             fn = getattr(lib, name)

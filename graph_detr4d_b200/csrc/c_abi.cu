@@ -140,4 +140,14 @@ int gd4d_pack_nchw(const void* src, void* dst, int32_t src_dtype, int32_t dst_dt
                              static_cast<cudaStream_t>(cuda_stream));
 }
 
+int gd4d_unpack_nhwc(const float* src, float* dst, int64_t images, int32_t C, int32_t H, int32_t W,
+                     void* cuda_stream) {
+  if (src == nullptr || dst == nullptr) return GD4D_ERR_NULL;
+  if (images <= 0 || C <= 0 || H <= 0 || W <= 0) return GD4D_ERR_DIMS;
+  // the pack kernels are a batched 2-D transpose (rows x cols -> cols x rows): the inverse is the
+  // same transpose with the roles of the channel axis and the pixel axis swapped
+  return gd4d::dispatch_pack(src, dst, GD4D_F32, GD4D_F32, images, H * W, C, 1,
+                             static_cast<cudaStream_t>(cuda_stream));
+}
+
 }  // extern "C"

@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 add_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xbias,
                          const float* __restrict__ r1, const float* __restrict__ r2,
                          const float* __restrict__ gamma,
-                         const float* __restrict__ beta, float* __restrict__ y,
+                         const float* __restrict__ beta, const float* __restrict__ pos,
+                         float* __restrict__ y, float* __restrict__ y2,
                          float* __restrict__ s_out, float* __restrict__ mean_out,
                          float* __restrict__ rstd_out, int64_t rows, float eps, bool relu) {
   constexpr int C = NV * 128;
@@ -136,12 +137,18 @@ add_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
     o.w = (v[j].w - mean) * rstd * g.w + b.w;
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     *reinterpret_cast<float4*>(y + base + c) = o;
+    if (y2 != nullptr) {  // second output y + pos: the next block's "query + query_pos"
+      const float4 q = *reinterpret_cast<const float4*>(pos + base + c);
+      o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+      *reinterpret_cast<float4*>(y2 + base + c) = o;
+    }
   }
 }
 
 template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32)
-add_layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ s,
+add_layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2,
+                         const float* __restrict__ s,
                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                          const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* __restrict__ gs, float* __restrict__ g_masked, int64_t rows,
@@ -159,6 +166,10 @@ add_layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__
     const int c = (j * 32 + lane) * 4;
     const float4 sv = *reinterpret_cast<const float4*>(s + base + c);
     float4 g = *reinterpret_cast<const float4*>(gy + base + c);
+    if (gy2 != nullptr) {  // gradient of the second output (y + pos)
+      const float4 h = *reinterpret_cast<const float4*>(gy2 + base + c);
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    }
     const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
     xh[j][0] = (sv.x - mean) * rstd; xh[j][1] = (sv.y - mean) * rstd;
     xh[j][2] = (sv.z - mean) * rstd; xh[j][3] = (sv.w - mean) * rstd;
@@ -169,8 +180,9 @@ add_layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__
       if (!((sv.y - mean) * rstd * gm.y + b.y > 0.f)) g.y = 0.f;
       if (!((sv.z - mean) * rstd * gm.z + b.z > 0.f)) g.z = 0.f;
       if (!((sv.w - mean) * rstd * gm.w + b.w > 0.f)) g.w = 0.f;
-      if (g_masked != nullptr) *reinterpret_cast<float4*>(g_masked + base + c) = g;
     }
+    // the EFFECTIVE incoming gradient (masked and/or summed), for the deferred gamma/beta reduction
+    if (g_masked != nullptr) *reinterpret_cast<float4*>(g_masked + base + c) = g;
     a[j][0] = g.x * gm.x; a[j][1] = g.y * gm.y; a[j][2] = g.z * gm.z; a[j][3] = g.w * gm.w;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { c1 += a[j][i]; c2 += a[j][i] * xh[j][i]; }
@@ -237,9 +249,11 @@ int gd4d_bias_act(float* y, const float* bias, int64_t rows, int32_t C, int32_t 
 }
 
 int gd4d_add_layernorm_fwd(const float* x, const float* xbias, const float* r1, const float* r2,
-                           const float* gamma, const float* beta, float* y, float* s_out,
-                           float* mean, float* rstd, int64_t rows, int32_t C, float eps,
-                           int32_t relu, void* cuda_stream) {
+                           const float* gamma, const float* beta, const float* pos, float* y,
+                           float* y2, float* s_out, float* mean, float* rstd, int64_t rows,
+                           int32_t C, float eps, int32_t relu, void* cuda_stream) {
+  if ((pos == nullptr) != (y2 == nullptr)) return GD4D_ERR_NULL;
+  if (!gd4d::al16(pos) || !gd4d::al16(y2)) return GD4D_ERR_ALIGN;
   if (x == nullptr || gamma == nullptr || beta == nullptr || y == nullptr || mean == nullptr ||
       rstd == nullptr)
     return GD4D_ERR_NULL;
@@ -253,8 +267,9 @@ int gd4d_add_layernorm_fwd(const float* x, const float* xbias, const float* r1, 
   const int block = gd4d::kLnWarps * 32;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
 #define GD4D_LN_FWD(NV)                                                                          \
-  gd4d::add_layernorm_fwd_kernel<NV><<<grid, block, 0, st>>>(x, xbias, r1, r2, gamma, beta, y, \
-                                                             s_out, mean, rstd, rows, eps, relu != 0)
+  gd4d::add_layernorm_fwd_kernel<NV><<<grid, block, 0, st>>>(x, xbias, r1, r2, gamma, beta, pos, y, \
+                                                             y2, s_out, mean, rstd, rows, eps,       \
+                                                             relu != 0)
   switch (C / 128) {
     case 1: GD4D_LN_FWD(1); break;
     case 2: GD4D_LN_FWD(2); break;
@@ -269,22 +284,23 @@ int gd4d_add_layernorm_fwd(const float* x, const float* xbias, const float* r1, 
   return gd4d::launched();
 }
 
-int gd4d_add_layernorm_bwd(const float* gy, const float* s, const float* mean, const float* rstd,
+int gd4d_add_layernorm_bwd(const float* gy, const float* gy2, const float* s, const float* mean,
+                           const float* rstd,
                            const float* gamma, const float* beta, float* gs, float* g_masked,
                            int64_t rows, int32_t C, int32_t relu, void* cuda_stream) {
   if (gy == nullptr || s == nullptr || mean == nullptr || rstd == nullptr || gamma == nullptr ||
       gs == nullptr || (relu && beta == nullptr))
     return GD4D_ERR_NULL;
   if (rows <= 0 || rows > (1LL << 31) || C <= 0 || C % 128 != 0 || C > 1024) return GD4D_ERR_DIMS;
-  if (!gd4d::al16(gy) || !gd4d::al16(s) || !gd4d::al16(gamma) || !gd4d::al16(beta) ||
+  if (!gd4d::al16(gy) || !gd4d::al16(gy2) || !gd4d::al16(s) || !gd4d::al16(gamma) || !gd4d::al16(beta) ||
       !gd4d::al16(gs) || !gd4d::al16(g_masked))
     return GD4D_ERR_ALIGN;
   const unsigned grid = static_cast<unsigned>((rows + gd4d::kLnWarps - 1) / gd4d::kLnWarps);
   const int block = gd4d::kLnWarps * 32;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
 #define GD4D_LN_BWD(NV)                                                                          \
-  gd4d::add_layernorm_bwd_kernel<NV><<<grid, block, 0, st>>>(gy, s, mean, rstd, gamma, beta, gs, \
-                                                             g_masked, rows, relu != 0)
+  gd4d::add_layernorm_bwd_kernel<NV><<<grid, block, 0, st>>>(gy, gy2, s, mean, rstd, gamma, beta, \
+                                                             gs, g_masked, rows, relu != 0)
   switch (C / 128) {
     case 1: GD4D_LN_BWD(1); break;
     case 2: GD4D_LN_BWD(2); break;

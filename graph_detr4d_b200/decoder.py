@@ -61,14 +61,14 @@ class SelfAttention(nn.Module):
         self.attn = nn.MultiheadAttention(embed_dims, num_heads, dropout)
         self.dropout_layer = nn.Dropout(dropout)
 
-    def branch(self, query, query_pos=None, defer_bias=False):
+    def branch(self, query, query_pos=None, defer_bias=False, qk_in=None):
         """dropout(attention(query)) without the identity.  ``defer_bias``: returns
         ``(out_without_out_proj_bias, bias)`` for a consumer that adds the bias itself (only when
         dropout is inactive, else ``(out, None)``)."""
         if query.is_cuda:
             defer = defer_bias and not _dropout_active(self.dropout_layer) and \
                 can_defer_bias(query, self.attn.out_proj)
-            out = self_attention(query, query_pos, self.attn, out_bias=not defer)   # bmm+softmax path (glue.py)
+            out = self_attention(query, query_pos, self.attn, out_bias=not defer, qk_in=qk_in)   # glue.py
             if defer_bias:
                 return (out, self.attn.out_proj.bias) if defer else (self.dropout_layer(out), None)
         else:
@@ -112,7 +112,9 @@ class DecoderLayer(nn.Module):
         self.ffns = nn.ModuleList([FFN(embed_dims, feedforward_channels, dropout)])
         self.norms = nn.ModuleList([nn.LayerNorm(embed_dims) for _ in range(3)])
 
-    def forward(self, query, value, query_pos, reference_points, img_metas):
+    def forward(self, query, value, query_pos, reference_points, img_metas, q_plus_pos=None, want_next=False):
+        """``q_plus_pos``: ``query + query_pos`` if the previous layer already produced it;
+        ``want_next``: also return ``output + query_pos`` for the next layer -> (output, output + pos)."""
         # post-norm layer: every "branch + identity" sum is folded into the LayerNorm that
         # follows it (fused.add_layernorm: one launch) when the tensors are CUDA fp32
         fuse = all(fused.can_fuse_layernorm(query, n) for n in self.norms)
@@ -122,14 +124,18 @@ class DecoderLayer(nn.Module):
             query = cross(query, None, value, None, query_pos=query_pos,
                           reference_points=reference_points, img_metas=img_metas)
             query = fast_layer_norm(query, self.norms[1])
-            return fast_layer_norm(self.ffns[0](query), self.norms[2])
-        out, bias = self.attentions[0].branch(query, query_pos, defer_bias=True)
-        query = fused.add_layernorm(out, self.norms[0], query, xbias=bias)
+            out = fast_layer_norm(self.ffns[0](query), self.norms[2])
+            return (out, None) if want_next else out
+        # every LayerNorm whose output feeds an attention block also emits output + query_pos
+        out, bias = self.attentions[0].branch(query, query_pos, defer_bias=True, qk_in=q_plus_pos)
+        query, qp = fused.add_layernorm(out, self.norms[0], query, xbias=bias, pos=query_pos)
         out, res, pos, bias = cross.forward_parts(query, None, value, None, query_pos=query_pos,
                                                   reference_points=reference_points, img_metas=img_metas,
-                                                  defer_bias=True)
+                                                  defer_bias=True, query_with_pos=qp)
         query = fused.add_layernorm(out, self.norms[1], res, pos, xbias=bias)
         out, bias = self.ffns[0].branch(query, defer_bias=True)
+        if want_next:
+            return fused.add_layernorm(out, self.norms[2], query, xbias=bias, pos=query_pos)
         return fused.add_layernorm(out, self.norms[2], query, xbias=bias)
 
 
@@ -148,8 +154,13 @@ class Detr3DTransformerDecoder(nn.Module):
     def forward(self, query, value, query_pos, reference_points, reg_branches=None, img_metas=None):
         output = query
         intermediate, intermediate_ref = [], []
+        q_plus_pos = None
         for lid, layer in enumerate(self.layers):
-            output = layer(output, value, query_pos, reference_points, img_metas)
+            if lid + 1 < len(self.layers):
+                output, q_plus_pos = layer(output, value, query_pos, reference_points, img_metas,
+                                           q_plus_pos=q_plus_pos, want_next=True)
+            else:
+                output = layer(output, value, query_pos, reference_points, img_metas, q_plus_pos=q_plus_pos)
             if reg_branches is not None:                                    # :201-214
                 tmp = output.permute(1, 0, 2)
                 tmp = _run_branch(reg_branches[lid], tmp)

@@ -47,7 +47,7 @@ class DeferredWgrad:
             G = torch.stack([it[4] for it in its])                     # (n, M, N)
             X = torch.stack([it[5] for it in its])                     # (n, M, K)
             dW = torch.bmm(G.transpose(1, 2), X)                       # (n, N, K)
-            ones = G.new_ones(1, 1, G.shape[1]).expand(G.shape[0], 1, G.shape[1])
+            ones = _ones_row(G, G.shape[1]).expand(G.shape[0], 1, G.shape[1])
             dB = torch.bmm(ones, G).squeeze(1)                         # (n, N): GEMV, not aten::sum (2-CTA reduce)
             for i, (wp, bp, r0, r1, _, _) in enumerate(its):
                 whole = r0 == 0 and r1 == wp.shape[0]
@@ -56,13 +56,21 @@ class DeferredWgrad:
                     if bp is not None:
                         bp.grad = dB[i] if bp.grad is None else bp.grad + dB[i]
                 else:                                                  # row slice of a packed parameter
-                    if id(wp) not in partial:
-                        partial[id(wp)] = (wp, bp, torch.zeros_like(wp),
-                                           torch.zeros_like(bp) if bp is not None else None)
-                    partial[id(wp)][2][r0:r1] += dW[i]
-                    if bp is not None:
-                        partial[id(wp)][3][r0:r1] += dB[i]
-        for wp, bp, gw, gb in partial.values():
+                    partial.setdefault(id(wp), (wp, bp, []))[2].append((r0, r1, dW[i], dB[i]))
+        for wp, bp, parts in partial.values():
+            parts.sort(key=lambda t: t[0])
+            tiles = parts[0][0] == 0 and parts[-1][1] == wp.shape[0] and \
+                all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            if tiles:                                                  # in_proj: [qk rows | v rows] -> one cat each
+                gw = torch.cat([t[2] for t in parts])
+                gb = torch.cat([t[3] for t in parts]) if bp is not None else None
+            else:
+                gw = torch.zeros_like(wp)
+                gb = torch.zeros_like(bp) if bp is not None else None
+                for r0, r1, dw, db in parts:
+                    gw[r0:r1] += dw
+                    if gb is not None:
+                        gb[r0:r1] += db
             wp.grad = gw if wp.grad is None else wp.grad + gw
             if bp is not None:
                 bp.grad = gb if bp.grad is None else bp.grad + gb
@@ -76,13 +84,27 @@ class DeferredWgrad:
             X = torch.stack([it[3] for it in its])
             mean = torch.stack([it[4] for it in its])                  # (n, M, 1)
             rstd = torch.stack([it[5] for it in its])
-            ones = G.new_ones(1, 1, G.shape[1]).expand(G.shape[0], 1, G.shape[1])
+            ones = _ones_row(G, G.shape[1]).expand(G.shape[0], 1, G.shape[1])
             dG = torch.bmm(ones, G * ((X - mean) * rstd)).squeeze(1)   # (n, C)
             dB = torch.bmm(ones, G).squeeze(1)
             for i, (wp, bp, *_rest) in enumerate(its):
                 wp.grad = dG[i] if wp.grad is None else wp.grad + dG[i]
                 bp.grad = dB[i] if bp.grad is None else bp.grad + dB[i]
         self.ln_items.clear()
+
+
+_ONES = {}
+
+
+def _ones_row(like: torch.Tensor, n: int) -> torch.Tensor:
+    """Persistent (1,1,n) row of ones per device/dtype (the GEMV that replaces aten::sum for bias
+    gradients): no fill launch per use."""
+    key = (like.device, like.dtype, n)
+    t = _ONES.get(key)
+    if t is None:
+        with torch.no_grad():
+            t = _ONES[key] = torch.ones(1, 1, n, device=like.device, dtype=like.dtype)
+    return t
 
 
 class _FastLinearFn(torch.autograd.Function):
@@ -121,7 +143,7 @@ class _FastLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = g2.t() @ x2
         if ctx.needs_input_grad[2]:
-            db = (g2.new_ones(1, g2.shape[0]) @ g2).view(-1)
+            db = (_ones_row(g2, g2.shape[0])[0] @ g2).view(-1)
         return dx, dw, db, None, None
 
 
@@ -156,7 +178,7 @@ class _LinearReluFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = g2.t() @ x2
         if ctx.needs_input_grad[2]:
-            db = (g2.new_ones(1, g2.shape[0]) @ g2).view(-1)
+            db = (_ones_row(g2, g2.shape[0])[0] @ g2).view(-1)
         return dx, dw, db, None
 
 
@@ -213,7 +235,7 @@ class _CatLinearFn(torch.autograd.Function):
             elif need:
                 if dwc is None:
                     dwc = g2.t() @ x2
-                    dbc = (g2.new_ones(1, g2.shape[0]) @ g2).view(-1)
+                    dbc = (_ones_row(g2, g2.shape[0])[0] @ g2).view(-1)
                 grads += [dwc[c0:c1], dbc[c0:c1]]
             else:
                 grads += [None, None]
@@ -365,7 +387,7 @@ class _AttnCoreFn(torch.autograd.Function):
         return dqk, dv, None, None
 
 
-def self_attention(query, query_pos, mha: torch.nn.MultiheadAttention, out_bias: bool = True):
+def self_attention(query, query_pos, mha: torch.nn.MultiheadAttention, out_bias: bool = True, qk_in=None):
     """nn.MultiheadAttention(q=k=query+pos, v=query), batch_first=False, eval/dropout-free
     math: explicit bmm + softmax (faster than the flash/mem-efficient kernels at L=900,
     head_dim 32, fp32).  Uses the module's own packed parameters."""
@@ -373,7 +395,8 @@ def self_attention(query, query_pos, mha: torch.nn.MultiheadAttention, out_bias:
     H = mha.num_heads
     d = E // H
     w, b = mha.in_proj_weight, mha.in_proj_bias
-    qk_in = query if query_pos is None else query + query_pos
+    if qk_in is None:                                   # else: the caller already has query + query_pos
+        qk_in = query if query_pos is None else query + query_pos
     own = w.requires_grad
     qk = _FastLinearFn.apply(qk_in, w[:2 * E], b[:2 * E], (w, b, 0, 2 * E) if own else None, True)  # (L,B,2E)
     v = _FastLinearFn.apply(query, w[2 * E:], b[2 * E:], (w, b, 2 * E, 3 * E) if own else None, True)  # (L,B,E)

@@ -335,17 +335,20 @@ class Detr3DCrossAtten(BaseModule):
 
     def forward_parts(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                       reference_points=None, spatial_shapes=None, level_start_index=None,
-                      defer_bias=False, **kwargs):
+                      defer_bias=False, query_with_pos=None, **kwargs):
         """The three addends of ``forward`` -- dropout(output_proj(sampled)), the residual and the
         position feature -- so that a caller that owns the following LayerNorm (decoder.py) can
         fold the sum into it (one launch).  With ``defer_bias`` a 4th item is returned: the
-        output_proj bias still to be added to the first addend (or None if it already was)."""
+        output_proj bias still to be added to the first addend (or None if it already was).
+        ``query_with_pos``: ``query + query_pos`` if the caller already has it."""
         if key is None:
             key = query
         if value is None:
             value = key
         inp_residual = query if residual is None else residual
-        if query_pos is not None:
+        if query_with_pos is not None:                      # caller already has query + query_pos (fused LN output)
+            query = query_with_pos
+        elif query_pos is not None:
             query = query + query_pos
         query = query.permute(1, 0, 2)                      # (B,Q,C)
         img_metas = kwargs["img_metas"]
@@ -423,17 +426,20 @@ class Detr3DCrossAttenV2(BaseModule):
 
     def forward_parts(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                       reference_points=None, spatial_shapes=None, level_start_index=None,
-                      defer_bias=False, **kwargs):
+                      defer_bias=False, query_with_pos=None, **kwargs):
         """The three addends of ``forward`` -- dropout(output_proj(sampled)), the residual and the
         position feature -- so that a caller that owns the following LayerNorm (decoder.py) can
         fold the sum into it (one launch).  With ``defer_bias`` a 4th item is returned: the
-        output_proj bias still to be added to the first addend (or None if it already was)."""
+        output_proj bias still to be added to the first addend (or None if it already was).
+        ``query_with_pos``: ``query + query_pos`` if the caller already has it."""
         if key is None:
             key = query
         if value is None:
             value = key
         inp_residual = query if residual is None else residual
-        if query_pos is not None:
+        if query_with_pos is not None:                      # caller already has query + query_pos (fused LN output)
+            query = query_with_pos
+        elif query_pos is not None:
             query = query + query_pos
         query = query.permute(1, 0, 2)
         img_metas = kwargs["img_metas"]
@@ -540,17 +546,20 @@ class Deform3DCrossAttn(BaseModule):
 
     def forward_parts(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                       reference_points=None, spatial_shapes=None, level_start_index=None,
-                      defer_bias=False, **kwargs):
+                      defer_bias=False, query_with_pos=None, **kwargs):
         """The three addends of ``forward`` -- dropout(output_proj(sampled)), the residual and the
         position feature -- so that a caller that owns the following LayerNorm (decoder.py) can
         fold the sum into it (one launch).  With ``defer_bias`` a 4th item is returned: the
-        output_proj bias still to be added to the first addend (or None if it already was)."""
+        output_proj bias still to be added to the first addend (or None if it already was).
+        ``query_with_pos``: ``query + query_pos`` if the caller already has it."""
         if key is None:
             key = query
         if value is None:
             value = key
         inp_residual = query if residual is None else residual
-        if query_pos is not None:
+        if query_with_pos is not None:                      # caller already has query + query_pos (fused LN output)
+            query = query_with_pos
+        elif query_pos is not None:
             query = query + query_pos
         query = query.permute(1, 0, 2)                      # (B,Q,C)
         img_metas = kwargs["img_metas"]

@@ -153,7 +153,7 @@ class _SinkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sink: GradSink, *feats: torch.Tensor):
         ctx.sink = sink
-        ctx.meta = [(tuple(f.shape), f.dtype) for f in feats]
+        ctx.meta = [(tuple(f.shape), f.dtype, f.is_contiguous()) for f in feats]
         return feats[0].new_zeros(())
 
     @staticmethod
@@ -162,9 +162,19 @@ class _SinkFn(torch.autograd.Function):
         if bufs is None:
             return (None,) + (None,) * len(ctx.meta)
         outs = []
-        for buf, (shape, dtype) in zip(bufs, ctx.meta):
-            g = buf.permute(0, 3, 1, 2).unflatten(0, shape[:2])
-            outs.append(g if g.dtype == dtype else g.to(dtype))
+        for buf, (shape, dtype, nchw) in zip(bufs, ctx.meta):
+            if nchw and dtype == torch.float32:
+                # NCHW producer: one tiled transpose (gd4d_unpack_nhwc) instead of the strided
+                # elementwise copy autograd would make to match the leaf's / conv's layout
+                g = torch.empty(shape, device=buf.device, dtype=torch.float32)
+                st = _lib.load().gd4d_unpack_nhwc(buf.data_ptr(), g.data_ptr(), shape[0] * shape[1], shape[2],
+                                                  shape[3], shape[4], _stream_ptr(buf.device))
+                _lib.check(st, "gd4d_unpack_nhwc")
+                _count()
+            else:                                          # channels-last producer: a view, no copy
+                g = buf.permute(0, 3, 1, 2).unflatten(0, shape[:2])
+                g = g if g.dtype == dtype else g.to(dtype)
+            outs.append(g)
         return (None, *outs)
 
 

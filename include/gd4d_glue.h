@@ -51,21 +51,23 @@ GD4D_API int gd4d_bias_act(float* y, const float* bias, int64_t rows, int32_t C,
                            void* cuda_stream);
 
 /* s = x + xbias + r1 + r2 (xbias (C) broadcast over rows; xbias, r1, r2 optional);
- * y = LayerNorm_C(s) * gamma + beta;  y = max(y,0) if relu.
+ * y = LayerNorm_C(s) * gamma + beta;  y = max(y,0) if relu;  y2 = y + pos (pos, y2 optional,
+ * both or neither: the "query + query_pos" the next attention block starts with).
  * Writes y (rows,C), mean/rstd (rows) and s (s_out is required whenever s != x).
  * C must be a multiple of 128 and <= 1024; all row pointers 16-byte aligned. */
 GD4D_API int gd4d_add_layernorm_fwd(const float* x, const float* xbias, const float* r1,
                                     const float* r2, const float* gamma, const float* beta,
-                                    float* y, float* s_out, float* mean, float* rstd,
-                                    int64_t rows, int32_t C, float eps, int32_t relu,
-                                    void* cuda_stream);
-/* gs = dL/ds (the same gradient flows to x, r1 and r2).  With relu the incoming gradient is
- * first masked by [y > 0] (recomputed from s, mean, rstd, gamma, beta) and, if g_masked != NULL,
- * the masked gradient is written out for the deferred gamma/beta reduction. */
-GD4D_API int gd4d_add_layernorm_bwd(const float* gy, const float* s, const float* mean,
-                                    const float* rstd, const float* gamma, const float* beta,
-                                    float* gs, float* g_masked, int64_t rows, int32_t C,
+                                    const float* pos, float* y, float* y2, float* s_out,
+                                    float* mean, float* rstd, int64_t rows, int32_t C, float eps,
                                     int32_t relu, void* cuda_stream);
+/* gs = dL/ds for the incoming gradient gy (+ gy2, the gradient of y2, optional); the same gs
+ * flows to x, r1 and r2.  With relu the incoming gradient is first masked by [y > 0] (recomputed
+ * from s, mean, rstd, gamma, beta).  If g_masked != NULL the effective incoming gradient
+ * (summed and/or masked) is written out for the deferred gamma/beta reduction. */
+GD4D_API int gd4d_add_layernorm_bwd(const float* gy, const float* gy2, const float* s,
+                                    const float* mean, const float* rstd, const float* gamma,
+                                    const float* beta, float* gs, float* g_masked, int64_t rows,
+                                    int32_t C, int32_t relu, void* cuda_stream);
 
 /* AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected, step counter on
  * the device so the launch is CUDA-graph capturable) over MANY tensors in ONE launch.

@@ -170,6 +170,12 @@ GD4D_API int gd4d_xview_backward(const gd4d_xview_params* p, void* cuda_stream);
 GD4D_API int gd4d_pack_nchw(const void* src, void* dst, int32_t src_dtype, int32_t dst_dtype,
                    int64_t images, int32_t C, int32_t H, int32_t W, void* cuda_stream);
 
+/* Inverse of gd4d_pack_nchw for fp32: channel-last (images, H, W, C) -> NCHW (images, C, H, W).
+ * Hands the shared feature-gradient map back to an NCHW producer (the FPN) in one tiled
+ * transpose instead of a strided elementwise copy. */
+GD4D_API int gd4d_unpack_nhwc(const float* src, float* dst, int64_t images, int32_t C, int32_t H,
+                     int32_t W, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,10 +74,13 @@ def test_launch_info_and_status_codes():
     assert lib.gd4d_inverse_sigmoid_bwd(0x1000, 0x1000, 0x1000, 0, 1e-5, 0, None) == -2
     assert lib.gd4d_ref_update(0x1000, 4, 0x1000, 0x1000, 10, 1e-5, None) == -2      # reg_stride < 5
     a = 0x1000
-    assert lib.gd4d_add_layernorm_fwd(a, None, None, None, a, a, a, None, a, a, 900, 200, 1e-5, 0, None) == -2
-    assert lib.gd4d_add_layernorm_fwd(a + 4, None, None, None, a, a, a, None, a, a, 900, 256, 1e-5, 0, None) == -4
-    assert lib.gd4d_add_layernorm_fwd(a, a, None, None, a, a, a, None, a, a, 900, 256, 1e-5, 0, None) == -1  # s_out
+    ln = lib.gd4d_add_layernorm_fwd          # x, xbias, r1, r2, gamma, beta, pos, y, y2, s_out, mean, rstd, ...
+    assert ln(a, None, None, None, a, a, None, a, None, None, a, a, 900, 200, 1e-5, 0, None) == -2
+    assert ln(a + 4, None, None, None, a, a, None, a, None, None, a, a, 900, 256, 1e-5, 0, None) == -4
+    assert ln(a, a, None, None, a, a, None, a, None, None, a, a, 900, 256, 1e-5, 0, None) == -1    # s_out
+    assert ln(a, None, None, None, a, a, a, a, None, None, a, a, 900, 256, 1e-5, 0, None) == -1    # pos w/o y2
     assert lib.gd4d_bias_act(a, a, 900, 10, 1, None) == -2                                      # C % 4
-    assert lib.gd4d_add_layernorm_bwd(a, a, a, a, a, None, a, None, 900, 256, 1, None) == -1   # relu needs beta
+    assert lib.gd4d_add_layernorm_bwd(a, None, a, a, a, a, None, a, None, 900, 256, 1, None) == -1   # relu needs beta
+    assert lib.gd4d_unpack_nhwc(a, None, 1, 1, 1, 1, None) == -1
     for code in (0, -1, -2, -3, -4, -5, -6, -99):
         assert len(_lib.strerror(code)) > 0

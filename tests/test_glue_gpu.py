@@ -212,3 +212,43 @@ def test_multi_tensor_adamw_matches_torch_adamw():
         assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max()) + 1e-7, i
     assert torch.equal(pb[skip].detach().cpu(), base[skip])
     assert float(ob.step_t) == 6.0
+
+
+@pytest.mark.parametrize("use", ["both", "y_only", "y2_only"])
+def test_add_layernorm_second_output_with_pos(use):
+    """(y, y + pos) in one launch; the backward sums the two incoming gradients in the kernel and
+    the deferred gamma/beta reduction sees the summed gradient."""
+    g = torch.Generator().manual_seed(41)
+    C, rows = 256, 900
+    x, r, pos = (torch.randn(rows, 1, C, generator=g) for _ in range(3))
+    ln = torch.nn.LayerNorm(C)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(C, generator=g)); ln.bias.copy_(torch.randn(C, generator=g))
+    g1, g2 = torch.randn(rows, 1, C, generator=g), torch.randn(rows, 1, C, generator=g)
+
+    def loss(y, y2):
+        return {"both": (y * g1.to(y.device)).sum() + (y2 * g2.to(y.device)).sum(),
+                "y_only": (y * g1.to(y.device)).sum(), "y2_only": (y2 * g2.to(y.device)).sum()}[use]
+
+    xo, ro, po = (t.clone().requires_grad_(True) for t in (x, r, pos))
+    yo = F.layer_norm(xo + ro, (C,), ln.weight, ln.bias)
+    loss(yo, yo + po).backward()
+    lng = torch.nn.LayerNorm(C).cuda()
+    lng.load_state_dict(ln.state_dict())
+    for deferred in (False, True):
+        lng.zero_grad(set_to_none=True)
+        xg, rg, pg = (t.cuda().requires_grad_(True) for t in (x, r, pos))
+        y, y2 = fused.add_layernorm(xg, lng, rg, pos=pg)
+        assert _rel(y.detach(), yo.detach()) <= TOL and _rel(y2.detach(), (yo + po).detach()) <= TOL
+        if deferred:
+            with DeferredWgrad() as wq:
+                loss(y, y2).backward()
+                wq.flush()
+        else:
+            loss(y, y2).backward()
+        assert _rel(xg.grad, xo.grad) <= 5e-5 and _rel(rg.grad, ro.grad) <= 5e-5
+        if use == "y_only":
+            assert pg.grad is None
+        else:
+            assert _rel(pg.grad, po.grad) <= TOL
+        assert _rel(lng.weight.grad, ln.weight.grad) <= 5e-5 and _rel(lng.bias.grad, ln.bias.grad) <= 5e-5

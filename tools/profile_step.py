@@ -37,3 +37,16 @@ ours = sum(r[0] for r in rows if "gd4d::" in r[2])
 print(f"libgd4d_xview.so kernels: {ours/1e3:.3f} ms ({100*ours/tot:.1f}%), {sum(r[1] for r in rows if 'gd4d::' in r[2]):.0f} launches")
 for t, n, k in rows[:70]:
     print(f"{t:9.1f} us {100*t/tot:5.1f}% n={n:6.1f} {k[:150]}")
+
+# ---- which tensors do the elementwise/copy launches touch? (aten op + input shapes) -------------------
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof2:
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+rows = []
+for e in prof2.key_averages(group_by_input_shape=True):
+    if e.key in ("aten::copy_", "aten::add", "aten::add_", "aten::fill_", "aten::zero_", "aten::cat", "aten::mul",
+                 "aten::sum", "aten::stack", "aten::contiguous", "aten::clone") and e.self_device_time_total > 0:
+        rows.append((e.self_device_time_total / 3.0, e.count / 3, e.key, str(e.input_shapes)[:120]))
+print("\n== elementwise / copy ops by input shape (self device time per step) ==")
+for t, n, k, sh in sorted(rows, reverse=True)[:40]:
+    print(f"{t:9.1f} us n={n:5.1f} {k:14s} {sh}")
