@@ -151,9 +151,30 @@ class Detr3DTransformerDecoder(nn.Module):
         self.return_intermediate = return_intermediate
         self.embed_dims = embed_dims
 
+    @torch.no_grad()
+    def _refresh_generator_packs(self, query):
+        """One multi-tensor copy refreshes EVERY layer's packed generator weights (the three
+        generator Linears run as one GEMM, modules.Deform3DCrossAttn) instead of two
+        concatenations per layer."""
+        if not (fused.ENABLED and query.is_cuda and query.dtype == torch.float32):
+            return
+        dsts, srcs, mods = [], [], []
+        for layer in self.layers:
+            m = layer.attentions[1]
+            if hasattr(m, "generator_pack_slots"):
+                d, s = m.generator_pack_slots()
+                dsts += d
+                srcs += [p.detach() for p in s]
+                mods.append(m)
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)
+            for m in mods:
+                m._gen_pack_fresh = True
+
     def forward(self, query, value, query_pos, reference_points, reg_branches=None, img_metas=None):
         output = query
         intermediate, intermediate_ref = [], []
+        self._refresh_generator_packs(query)
         q_plus_pos = None
         for lid, layer in enumerate(self.layers):
             if lid + 1 < len(self.layers):
@@ -202,6 +223,9 @@ class Detr3DTransformer(nn.Module):
     def forward(self, mlvl_feats, img_metas, batch_size: int):
         query_embed = self.query_embedding.weight
         query_pos, query = torch.split(query_embed, self.embed_dims, dim=1)
+        # the two halves are row-strided views of the (Q, 2C) embedding: make them dense ONCE per
+        # forward instead of once per consumer (every fused kernel needs dense rows)
+        query_pos, query = query_pos.contiguous(), query.contiguous()
         query_pos = query_pos.unsqueeze(0).expand(batch_size, -1, -1)
         query = query.unsqueeze(0).expand(batch_size, -1, -1)
         reference_points = fast_linear(query_pos, self.reference_points).sigmoid()   # NOT detached in layer 0

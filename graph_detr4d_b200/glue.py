@@ -43,7 +43,12 @@ class DeferredWgrad:
             g2, x2 = it[4], it[5]
             groups.setdefault((g2.shape[0], g2.shape[1], x2.shape[1]), []).append(it)
         partial = {}
+        gid = 0
         for (_, _, _), its in groups.items():
+            gid += 1
+            # row-slice items (packed parameters) first, in encounter order: their results are then
+            # consecutive slices of dW / dB in the same module order in every group (see below)
+            its.sort(key=lambda it: 0 if not (it[2] == 0 and it[3] == it[0].shape[0]) else 1)
             G = torch.stack([it[4] for it in its])                     # (n, M, N)
             X = torch.stack([it[5] for it in its])                     # (n, M, K)
             dW = torch.bmm(G.transpose(1, 2), X)                       # (n, N, K)
@@ -56,12 +61,46 @@ class DeferredWgrad:
                     if bp is not None:
                         bp.grad = dB[i] if bp.grad is None else bp.grad + dB[i]
                 else:                                                  # row slice of a packed parameter
-                    partial.setdefault(id(wp), (wp, bp, []))[2].append((r0, r1, dW[i], dB[i]))
-        for wp, bp, parts in partial.values():
+                    partial.setdefault(id(wp), (wp, bp, []))[2].append((r0, r1, dW[i], dB[i], gid, i, dW, dB))
+        # Packed parameters whose row slices tile them exactly (nn.MultiheadAttention.in_proj:
+        # [q,k rows | v rows]) and sit at CONSECUTIVE indices of the same batched results across
+        # modules (layer after layer): ONE cat along the row axis for all of them.
+        batched = {}
+        for key, (wp, bp, parts) in partial.items():
             parts.sort(key=lambda t: t[0])
             tiles = parts[0][0] == 0 and parts[-1][1] == wp.shape[0] and \
                 all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
-            if tiles:                                                  # in_proj: [qk rows | v rows] -> one cat each
+            sig = (tiles, bp is not None, tuple((t[0], t[1], t[4]) for t in parts))
+            batched.setdefault(sig, []).append(key)
+        done = set()
+        for sig, keys in batched.items():
+            if not sig[0] or len(keys) < 2:
+                continue
+            plists = [partial[k][2] for k in keys]
+            nparts = len(plists[0])
+            idx = [[pl[j][5] for pl in plists] for j in range(nparts)]          # per part: batch indices
+            if not all(ix == list(range(ix[0], ix[0] + len(ix))) or ix == list(range(ix[0], ix[0] - len(ix), -1))
+                       for ix in idx):
+                continue
+            def take(t, ix):
+                lo, hi = min(ix), max(ix) + 1
+                v = t[lo:hi]
+                return v if ix[0] == lo else v.flip(0)
+            gw_all = torch.cat([take(plists[0][j][6], idx[j]) for j in range(nparts)], dim=1)   # (m, rows, K)
+            gb_all = torch.cat([take(plists[0][j][7], idx[j]) for j in range(nparts)], dim=1) if sig[1] else None
+            for m, k in enumerate(keys):
+                wp, bp, _ = partial[k]
+                wp.grad = gw_all[m] if wp.grad is None else wp.grad + gw_all[m]
+                if bp is not None:
+                    bp.grad = gb_all[m] if bp.grad is None else bp.grad + gb_all[m]
+                done.add(k)
+        for key, (wp, bp, parts) in partial.items():
+            if key in done:
+                continue
+            parts = [t[:4] for t in parts]
+            tiles = parts[0][0] == 0 and parts[-1][1] == wp.shape[0] and \
+                all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            if tiles:                                                  # [qk rows | v rows] -> one cat each
                 gw = torch.cat([t[2] for t in parts])
                 gb = torch.cat([t[3] for t in parts]) if bp is not None else None
             else:
@@ -198,18 +237,23 @@ class _CatLinearFn(torch.autograd.Function):
     """Several Linears on the SAME input as ONE GEMM over their concatenated weights:
     y (.., width) = x @ cat(W_i)^T + cat(b_i), columns padded with zeros to ``width``.
     Backward: one dX GEMM; each Linear's weight/bias gradient is its column block of G^T X
-    (deferred and batched under DeferredWgrad).  inputs: x, width, *(w0, b0, w1, b1, ...)."""
+    (deferred and batched under DeferredWgrad).  inputs: x, width, packed, *(w0, b0, w1, b1, ...);
+    ``packed`` = (W_cat, b_cat) if the caller keeps an up-to-date packed copy of the weights
+    (decoder.py refreshes all layers' copies with one multi-tensor launch per forward), else None."""
 
     @staticmethod
-    def forward(ctx, x, width: int, *wb):
+    def forward(ctx, x, width: int, packed, *wb):
         from . import fused
         ws, bs = wb[0::2], wb[1::2]
         n = sum(int(w.shape[0]) for w in ws)
         K = x.shape[-1]
         pad = width - n
         x2 = x.reshape(-1, K)
-        wc = torch.cat(list(ws) + ([_pad_zeros(x, pad, K)] if pad else []))
-        bc = torch.cat(list(bs) + ([_pad_zeros(x, 1, pad).view(-1)] if pad else []))
+        if packed is not None:
+            wc, bc = packed
+        else:
+            wc = torch.cat(list(ws) + ([_pad_zeros(x, pad, K)] if pad else []))
+            bc = torch.cat(list(bs) + ([_pad_zeros(x, 1, pad).view(-1)] if pad else []))
         y = x.new_empty(*x.shape[:-1], width)
         torch.mm(x2, wc.t(), out=y.view(-1, width))
         fused.bias_act_(y, bc, relu=False)
@@ -228,7 +272,7 @@ class _CatLinearFn(torch.autograd.Function):
         dwc = dbc = None
         for i, (w, b) in enumerate(ctx.params):
             c1 = c0 + int(w.shape[0])
-            need = ctx.needs_input_grad[2 + 2 * i]
+            need = ctx.needs_input_grad[3 + 2 * i]
             if need and q is not None and w.is_leaf:
                 q.items.append((w, b, 0, int(w.shape[0]), g2[:, c0:c1], x2))
                 grads += [None, None]
@@ -240,15 +284,15 @@ class _CatLinearFn(torch.autograd.Function):
             else:
                 grads += [None, None]
             c0 = c1
-        return (dx, None, *grads)
+        return (dx, None, None, *grads)
 
 
-def cat_linear(x: torch.Tensor, lins, width: int) -> torch.Tensor:
+def cat_linear(x: torch.Tensor, lins, width: int, packed=None) -> torch.Tensor:
     """(.., width) = [lin_0(x) | lin_1(x) | ... | 0-padding], one GEMM (CUDA fp32 only)."""
     wb = []
     for lin in lins:
         wb += [lin.weight, lin.bias]
-    return _CatLinearFn.apply(x, int(width), *wb)
+    return _CatLinearFn.apply(x, int(width), packed, *wb)
 
 
 class _FastLayerNormFn(torch.autograd.Function):

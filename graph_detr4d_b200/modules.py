@@ -520,6 +520,32 @@ class Deform3DCrossAttn(BaseModule):
         _constant_(self.attention_weights, 0.0, 0.0)
         _xavier_uniform_(self.value_proj, 0.0)
 
+    _gen_pack = None
+    _gen_pack_fresh = False
+
+    def _generator_linears(self):
+        return (self.attention_weights, self.deform_sampling_offsets, self.cam_attention_weights)
+
+    def generator_pack_slots(self):
+        """(destination views, source parameters) of this module's packed generator weights
+        [attention_weights | deform_sampling_offsets | cam_attention_weights | zero pad].  A caller
+        that copies sources into destinations (decoder.py: ONE multi-tensor copy for all layers)
+        and then sets ``_gen_pack_fresh`` lets the next forward skip its own two concatenations."""
+        lins = self._generator_linears()
+        n = sum(l.out_features for l in lins)
+        width = (n + 3) // 4 * 4
+        w0 = lins[0].weight
+        if self._gen_pack is None or self._gen_pack[0].device != w0.device:
+            with torch.no_grad():
+                self._gen_pack = (w0.new_zeros(width, w0.shape[1]), w0.new_zeros(width))
+        wc, bc = self._gen_pack
+        dsts, srcs, o = [], [], 0
+        for l in lins:
+            dsts += [wc[o:o + l.out_features], bc[o:o + l.out_features]]
+            srcs += [l.weight, l.bias]
+            o += l.out_features
+        return dsts, srcs
+
     def _use_wide(self, packed: PackedFeatures) -> bool:
         row_bytes = packed.C * packed.levels[0].element_size()
         return self.value_proj_mode == "fused" and row_bytes in (512, 1024)
@@ -577,8 +603,9 @@ class Deform3DCrossAttn(BaseModule):
             n_off = self.num_heads * self.num_points * 3
             layout = ops.GenLayout(cam=n_attn + n_off, offsets=n_attn, attn=0,
                                    width=(n_attn + n_off + self.num_cams + 3) // 4 * 4)
-            gen = cat_linear(query, (self.attention_weights, self.deform_sampling_offsets,
-                                     self.cam_attention_weights), layout.width)          # (B,Q,width)
+            fresh, self._gen_pack_fresh = self._gen_pack_fresh, False
+            gen = cat_linear(query, self._generator_linears(), layout.width,
+                             packed=self._gen_pack if fresh else None)                   # (B,Q,width)
 
             def sample(cfg, values=None):
                 return ops.xview_attention_gen(cfg, packed, reference_points, gen, layout, l2i, values=values)
