@@ -302,7 +302,8 @@ def main():
     sampler = ClockSampler(local_rank)                      # 200 ms period (B200_PROFILING.md): started before
     sampler.start()                                         # the warm-up so short timed regions still get samples
     t_pre = time.time()                                     # untimed pre-warm (~2 s of replays): the first
-    while time.time() - t_pre < 2.0:                        # seconds after context creation run 3-5 % slow
+    prewarm_s = float(os.environ.get("GD4D_BENCH_PREWARM", "2.0"))   # 0 under ncu (every replayed kernel is profiled)
+    while time.time() - t_pre < prewarm_s:                  # seconds after context creation run 3-5 % slow
         for _ in range(20):                                 # (r1: same process-fresh box, 5.28 -> 5.04 ms/step)
             step_resident()
         torch.cuda.synchronize()

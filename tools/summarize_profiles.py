@@ -33,7 +33,7 @@ def launches(path, prefix):
     with gzip.open(prefix + "_launch_list.csv.gz", "wt") as f:
         f.writelines(lines)
     names = [r["Kernel Name"] for r in rows]
-    adam = [i for i, n in enumerate(names) if "FusedAd" in n]
+    adam = [i for i, n in enumerate(names) if "FusedAd" in n or "adamw_multi" in n]   # last kernel of a step
     groups = []
     for i in adam:
         if groups and i - groups[-1][-1] <= 3:
