@@ -28,6 +28,11 @@ class DeferredWgrad:
     def __init__(self):
         self.items = []        # (weight_param, bias_param, row0, row1, g2, x2)
         self.ln_items = []     # (weight_param, bias_param, g2, x2, mean, rstd)
+        # after flush(): the few large contiguous result buffers, and the ids of the parameters whose
+        # .grad is a view into one of them -- a data-parallel caller all-reduces THESE instead of
+        # gathering ~200 gradient tensors into a flat buffer first (graphed.GraphedTrainStep)
+        self.buffers = []
+        self.covered = set()
 
     def __enter__(self):
         DeferredWgrad._active = self
@@ -54,12 +59,15 @@ class DeferredWgrad:
             dW = torch.bmm(G.transpose(1, 2), X)                       # (n, N, K)
             ones = _ones_row(G, G.shape[1]).expand(G.shape[0], 1, G.shape[1])
             dB = torch.bmm(ones, G).squeeze(1)                         # (n, N): GEMV, not aten::sum (2-CTA reduce)
+            n_part = sum(1 for it in its if not (it[2] == 0 and it[3] == it[0].shape[0]))
+            if n_part < len(its):
+                self.buffers += [dW[n_part:], dB[n_part:]]             # the whole-parameter results (contiguous)
             for i, (wp, bp, r0, r1, _, _) in enumerate(its):
                 whole = r0 == 0 and r1 == wp.shape[0]
                 if whole:
-                    wp.grad = dW[i] if wp.grad is None else wp.grad + dW[i]
+                    self._assign(wp, dW[i])
                     if bp is not None:
-                        bp.grad = dB[i] if bp.grad is None else bp.grad + dB[i]
+                        self._assign(bp, dB[i])
                 else:                                                  # row slice of a packed parameter
                     partial.setdefault(id(wp), (wp, bp, []))[2].append((r0, r1, dW[i], dB[i], gid, i, dW, dB))
         # Packed parameters whose row slices tile them exactly (nn.MultiheadAttention.in_proj:
@@ -88,11 +96,12 @@ class DeferredWgrad:
                 return v if ix[0] == lo else v.flip(0)
             gw_all = torch.cat([take(plists[0][j][6], idx[j]) for j in range(nparts)], dim=1)   # (m, rows, K)
             gb_all = torch.cat([take(plists[0][j][7], idx[j]) for j in range(nparts)], dim=1) if sig[1] else None
+            self.buffers += [gw_all] + ([gb_all] if gb_all is not None else [])
             for m, k in enumerate(keys):
                 wp, bp, _ = partial[k]
-                wp.grad = gw_all[m] if wp.grad is None else wp.grad + gw_all[m]
+                self._assign(wp, gw_all[m])
                 if bp is not None:
-                    bp.grad = gb_all[m] if bp.grad is None else bp.grad + gb_all[m]
+                    self._assign(bp, gb_all[m])
                 done.add(k)
         for key, (wp, bp, parts) in partial.items():
             if key in done:
@@ -126,10 +135,20 @@ class DeferredWgrad:
             ones = _ones_row(G, G.shape[1]).expand(G.shape[0], 1, G.shape[1])
             dG = torch.bmm(ones, G * ((X - mean) * rstd)).squeeze(1)   # (n, C)
             dB = torch.bmm(ones, G).squeeze(1)
+            self.buffers += [dG, dB]
             for i, (wp, bp, *_rest) in enumerate(its):
-                wp.grad = dG[i] if wp.grad is None else wp.grad + dG[i]
-                bp.grad = dB[i] if bp.grad is None else bp.grad + dB[i]
+                self._assign(wp, dG[i])
+                self._assign(bp, dB[i])
         self.ln_items.clear()
+
+    def _assign(self, param, grad_view):
+        """param.grad = view of a recorded buffer (covered), or accumulate (then no longer covered)."""
+        if param.grad is None:
+            param.grad = grad_view
+            self.covered.add(id(param))
+        else:
+            param.grad = param.grad + grad_view
+            self.covered.discard(id(param))
 
 
 _ONES = {}

@@ -27,7 +27,8 @@ from . import modules
 from .glue import DeferredWgrad
 from .optim import MultiTensorAdamW
 
-MULTI_TENSOR_ADAMW = os.environ.get("GD4D_MULTI_ADAMW", "1") != "0"      # A/B switch for measurements
+MULTI_TENSOR_ADAMW = os.environ.get("GD4D_MULTI_ADAMW", "1") != "0"      # A/B switches for measurements
+COALESCED_ALLREDUCE = os.environ.get("GD4D_COALESCED_ALLREDUCE", "1") != "0"
 
 
 class GraphedTrainStep:
@@ -42,14 +43,18 @@ class GraphedTrainStep:
         params = [p for p in model.parameters() if p.requires_grad]
         self.params = params
         n = sum(p.numel() for p in params)
-        # N > 1 only: ONE flat fp32 buffer for the gradient all-reduce.  Autograd is left to hand
-        # each parameter its freshly computed gradient (``p.grad = None`` before backward), which
-        # costs no kernel; accumulating into pre-set ``.grad`` views instead costs one
-        # elementwise add PER PARAMETER per step (~250 launches, ~0.7 ms of this step in r1).
-        # The fresh gradients are gathered into the flat buffer by a multi-tensor copy.
-        self.flat_grad = torch.zeros(n if world_size > 1 else 1, device=dev, dtype=torch.float32)
+        # Autograd is left to hand each parameter its freshly computed gradient (``p.grad = None``
+        # before backward), which costs no kernel; accumulating into pre-set ``.grad`` views instead
+        # costs one elementwise add PER PARAMETER per step (~250 launches, ~0.7 ms of this step in r1).
+        # N > 1: almost every gradient is a view into one of ~15 large batched result buffers of
+        # DeferredWgrad.flush(); those buffers (plus the few directly produced gradients) are
+        # all-reduced IN PLACE by one grouped NCCL launch.  (GD4D_COALESCED_ALLREDUCE=0: the r1
+        # scheme -- gather every gradient into ONE flat buffer with a multi-tensor copy, all-reduce it.)
+        flat = world_size > 1 and not COALESCED_ALLREDUCE
+        self.flat_grad = torch.zeros(n if flat else 1, device=dev, dtype=torch.float32)
         self.flat_views = []
-        if world_size > 1:
+        self._reduce: List[torch.Tensor] = []
+        if flat:
             o = 0
             for p in params:
                 self.flat_views.append(self.flat_grad[o:o + p.numel()].view_as(p))
@@ -74,10 +79,16 @@ class GraphedTrainStep:
                 loss.backward()
                 wq.flush()
             if self.world > 1:
-                have = [(v, p.grad) for v, p in zip(self.flat_views, params) if p.grad is not None]
-                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
-                for v, p in zip(self.flat_views, params):
-                    p.grad = v                             # the optimizer reads the (all-reduced) flat views
+                if COALESCED_ALLREDUCE:
+                    # all-reduce the few large batched result buffers in place, plus the handful of
+                    # gradients autograd produced directly: no gather copy, the optimizer reads p.grad
+                    self._reduce = list(wq.buffers) + [p.grad for p in params
+                                                       if p.grad is not None and id(p) not in wq.covered]
+                else:
+                    have = [(v, p.grad) for v, p in zip(self.flat_views, params) if p.grad is not None]
+                    torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+                    for v, p in zip(self.flat_views, params):
+                        p.grad = v                         # the optimizer reads the (all-reduced) flat views
             return loss.detach()
 
         side = torch.cuda.Stream(device=dev)
@@ -101,8 +112,15 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
 
     def _allreduce(self):
-        if self.world > 1:
+        if self.world <= 1:
+            return
+        if not COALESCED_ALLREDUCE:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+            return
+        # ONE grouped NCCL launch (ncclGroupStart/End) over ~20 tensors, in place
+        with dist.distributed_c10d._coalescing_manager():
+            for t in self._reduce:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG)
 
     def set_inputs(self, feats: Optional[Sequence[torch.Tensor]] = None, img_metas=None):
         """Stream-ordered refresh of the static inputs (H2D when ``feats`` are host tensors)."""

@@ -59,10 +59,19 @@ def _worker(rank, world, port, out):
     flat /= world
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
+    # grouped in-place all-reduce of several buffers (GraphedTrainStep's N > 1 scheme) == one by one
+    bufs = [torch.full((3, 4), float(rank + 1)), torch.arange(5.0) * (rank + 1), torch.ones(2, 2, 2) * rank]
+    want = [b.clone() for b in bufs]
+    for w in want:
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    with dist.distributed_c10d._coalescing_manager():
+        for b in bufs:
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    coalesced_ok = all(torch.equal(a, b) for a, b in zip(bufs, want))
     t = torch.tensor([10.0 + rank])                        # max-over-ranks timing reduction
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        torch.save(dict(avg=flat.clone(), locals=gathered, tmax=float(t)), out)
+        torch.save(dict(avg=flat.clone(), locals=gathered, tmax=float(t), coalesced_ok=coalesced_ok), out)
     dist.destroy_process_group()
 
 
@@ -71,7 +80,7 @@ def test_two_rank_gradient_allreduce(tmp_path):
     out = str(tmp_path / "r0.pt")
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     r = torch.load(out)
-    assert r["tmax"] == 11.0
+    assert r["tmax"] == 11.0 and r["coalesced_ok"]
     l0, l1 = r["locals"]
     assert not torch.equal(l0, l1)                         # ranks saw different scenes
     assert torch.allclose(r["avg"], (l0 + l1) / 2, rtol=0, atol=1e-6)
