@@ -28,22 +28,24 @@ def _build(variant, N, layers, factory=None, Q=80):
     return model
 
 
-@pytest.mark.parametrize("variant,T", [("A", 1), ("C", 2)])
-def test_decoder_matches_oracle_decoder(variant, T):
-    sc = H.scene(B=1, T=T, Q=80)
+@pytest.mark.parametrize("variant,T,B", [("A", 1, 1), ("C", 2, 1), ("A", 1, 2)])
+def test_decoder_matches_oracle_decoder(variant, T, B):
+    """B = 2 exercises the batch > 1 branches of the glue (generic self-attention path, strided
+    query_pos / residual rows in the fused LayerNorm, per-sample matrices)."""
+    sc = H.scene(B=B, T=T, Q=80)
     ref_model = _build(variant, sc["N"], 3, factory=build_oracle_attention)
     model = _build(variant, sc["N"], 3).cuda()
     model.load_state_dict(ref_model.state_dict(), strict=True)       # same parameter names
     feats_o = [f.clone().requires_grad_(True) for f in sc["feats"]]
-    st_o, r0_o, refs_o = ref_model(feats_o, sc["metas"], 1)
+    st_o, r0_o, refs_o = ref_model(feats_o, sc["metas"], B)
     # NOT mean(st^2): right after a LayerNorm that is a constant, its gradient is rounding noise
     gout = torch.randn(st_o.shape, generator=torch.Generator().manual_seed(5))
     (st_o * gout).sum().backward()
     feats_g = [f.cuda().requires_grad_(True) for f in sc["feats"]]
     g.clear_caches()
-    st, r0, refs = model(feats_g, sc["metas"], 1)
+    st, r0, refs = model(feats_g, sc["metas"], B)
     (st * gout.cuda()).sum().backward()
-    assert tuple(st.shape) == (3, 80, 1, 256) and tuple(refs.shape) == (3, 1, 80, 3)
+    assert tuple(st.shape) == (3, 80, B, 256) and tuple(refs.shape) == (3, B, 80, 3)
     assert H.rel_err(st.detach().cpu(), st_o.detach()) <= 2e-4      # 3 layers of fp32 GEMM-order noise
     assert H.rel_err(refs.detach().cpu(), refs_o.detach()) <= 2e-4
     for a, b in zip(feats_g, feats_o):
