@@ -1,4 +1,4 @@
-"""ctypes binding of libgd4d_xview.so (the C ABI in include/gd4d_xview.h and gd4d_glue.h).
+"""ctypes binding of libgd4d_xview.so (the C ABI in include/gd4d_xview.h, gd4d_glue.h and gd4d_frustum.h).
 
 There is deliberately NO fallback: if the shared library is missing or was not
 built for this GPU, every op raises.  ``load()`` builds in-tree with nvcc when the
@@ -37,6 +37,8 @@ EXPORTS = (
     "gd4d_add_layernorm_bwd",
     "gd4d_adamw_chunk",
     "gd4d_adamw_multi",
+    # include/gd4d_frustum.h
+    "gd4d_frustum_pe",
 )
 
 
@@ -132,7 +134,9 @@ def load(build_if_missing: bool = True):
                 ("gd4d_add_layernorm_fwd", [vp] * 12 + [i64, i32, f32, i32, vp]),
                 ("gd4d_add_layernorm_bwd", [vp] * 9 + [i64, i32, i32, vp]),
                 ("gd4d_adamw_chunk", []),
-                ("gd4d_adamw_multi", [vp, vp, i32, vp, f32, f32, f32, f32, f32, vp])):
+                ("gd4d_adamw_multi", [vp, vp, i32, vp, f32, f32, f32, f32, f32, vp]),
+                ("gd4d_frustum_pe", [vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32,
+                                     C.POINTER(C.c_float), vp])):
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = C.c_int, args
         lib.gd4d_params_size.restype = C.c_int

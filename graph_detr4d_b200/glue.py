@@ -151,18 +151,10 @@ class DeferredWgrad:
             self.covered.discard(id(param))
 
 
-_ONES = {}
-
-
 def _ones_row(like: torch.Tensor, n: int) -> torch.Tensor:
-    """Persistent (1,1,n) row of ones per device/dtype (the GEMV that replaces aten::sum for bias
-    gradients): no fill launch per use."""
-    key = (like.device, like.dtype, n)
-    t = _ONES.get(key)
-    if t is None:
-        with torch.no_grad():
-            t = _ONES[key] = torch.ones(1, 1, n, device=like.device, dtype=like.dtype)
-    return t
+    """(1,1,n) row of ones: the GEMV that replaces aten::sum for bias gradients."""
+    return _const(("ones", like.device, like.dtype, n),
+                  lambda: torch.ones(1, 1, n, device=like.device, dtype=like.dtype))
 
 
 class _FastLinearFn(torch.autograd.Function):
@@ -240,16 +232,9 @@ class _LinearReluFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
-_PAD = {}
-
-
 def _pad_zeros(like: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
-    key = (like.device, like.dtype, rows, cols)
-    z = _PAD.get(key)
-    if z is None:
-        with torch.no_grad():
-            z = _PAD[key] = torch.zeros(rows, cols, device=like.device, dtype=like.dtype)
-    return z
+    return _const(("pad", like.device, like.dtype, rows, cols),
+                  lambda: torch.zeros(rows, cols, device=like.device, dtype=like.dtype))
 
 
 class _CatLinearFn(torch.autograd.Function):
@@ -370,18 +355,25 @@ def linear_relu(x: torch.Tensor, lin: torch.nn.Linear) -> torch.Tensor:
     return _LinearReluFn.apply(x, lin.weight, lin.bias, owner)
 
 
-_ZEROS = {}
+_CONSTS = {}
+
+
+def _const(key, make):
+    """Persistent small constant tensors (no fill launch per use).  A constant first needed WHILE a
+    CUDA graph is being captured is not cached: its memory belongs to that graph's private pool."""
+    t = _CONSTS.get(key)
+    if t is None:
+        with torch.no_grad():
+            t = make()
+        if not (t.is_cuda and torch.cuda.is_current_stream_capturing()):
+            _CONSTS[key] = t
+    return t
 
 
 def _zero(like: torch.Tensor) -> torch.Tensor:
-    """A persistent (1,1,1) zero per device/dtype: baddbmm's ignored ``input`` (beta = 0) without
-    a fill launch per call."""
-    key = (like.device, like.dtype)
-    z = _ZEROS.get(key)
-    if z is None:
-        with torch.no_grad():
-            z = _ZEROS[key] = torch.zeros(1, 1, 1, device=like.device, dtype=like.dtype)
-    return z
+    """(1,1,1) zero: baddbmm's ignored ``input`` (beta = 0)."""
+    return _const(("zero", like.device, like.dtype),
+                  lambda: torch.zeros(1, 1, 1, device=like.device, dtype=like.dtype))
 
 
 class _ScaledBmmNT(torch.autograd.Function):

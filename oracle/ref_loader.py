@@ -241,3 +241,33 @@ def load():
         registries=_REGS,
     )
     return ns
+
+
+# ------------------------------------------------------------------------------------------
+# Detr3DHeadPE.position_embeding: executed unmodified as the pin
+# ------------------------------------------------------------------------------------------
+REF_HEAD_PE = os.path.join(REF_ROOT, "projects", "mmdet3d_plugin", "models", "dense_heads", "detr3d_head_pe.py")
+
+
+def load_position_embeding():
+    """The reference's ``Detr3DHeadPE.position_embeding`` (dense_heads/detr3d_head_pe.py:427-491) as
+    a plain function ``f(self, img_feats, img_metas, masks)``.  The method's FunctionDef is
+    AST-extracted from the file where it lies and compiled unmodified; the file itself cannot be
+    imported (mmcv / mmdet / mmdet3d are not installed).  Its one free name that is not numpy /
+    torch, ``inverse_sigmoid`` (imported there from mmdet 2.x, un-vendored, un-pinned), is bound to
+    the reference's OWN identical copy, detr3d_transformer.py:28-43."""
+    import ast
+    import numpy as np
+    src = open(REF_HEAD_PE).read()
+    tree = ast.parse(src)
+    fn = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == "Detr3DHeadPE":
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name == "position_embeding":
+                    fn = item
+    assert fn is not None, "reference source changed: Detr3DHeadPE.position_embeding not found"
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ns = {"np": np, "torch": torch, "inverse_sigmoid": load().inverse_sigmoid}
+    exec(compile(mod, REF_HEAD_PE, "exec"), ns)
+    return ns["position_embeding"]
