@@ -1,4 +1,4 @@
-"""ctypes binding of libgd4d_xview.so (the C ABI in include/gd4d_xview.h, gd4d_glue.h and gd4d_frustum.h).
+"""ctypes binding of libgd4d_xview.so (the C ABI in include/gd4d_xview.h, gd4d_glue.h, gd4d_frustum.h and gd4d_assign.h).
 
 There is deliberately NO fallback: if the shared library is missing or was not
 built for this GPU, every op raises.  ``load()`` builds in-tree with nvcc when the
@@ -39,6 +39,8 @@ EXPORTS = (
     "gd4d_adamw_multi",
     # include/gd4d_frustum.h
     "gd4d_frustum_pe",
+    # include/gd4d_assign.h
+    "gd4d_match_cost",
 )
 
 
@@ -136,7 +138,8 @@ def load(build_if_missing: bool = True):
                 ("gd4d_adamw_chunk", []),
                 ("gd4d_adamw_multi", [vp, vp, i32, vp, f32, f32, f32, f32, f32, vp]),
                 ("gd4d_frustum_pe", [vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32,
-                                     C.POINTER(C.c_float), vp])):
+                                     C.POINTER(C.c_float), vp]),
+                ("gd4d_match_cost", [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, f32, f32, vp])):
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = C.c_int, args
         lib.gd4d_params_size.restype = C.c_int

@@ -271,3 +271,55 @@ def load_position_embeding():
     ns = {"np": np, "torch": torch, "inverse_sigmoid": load().inverse_sigmoid}
     exec(compile(mod, REF_HEAD_PE, "exec"), ns)
     return ns["position_embeding"]
+
+
+# ------------------------------------------------------------------------------------------
+# HungarianAssigner3D: the reference's own class, executed unmodified
+# ------------------------------------------------------------------------------------------
+REF_BBOX = os.path.join(REF_ROOT, "projects", "mmdet3d_plugin", "core", "bbox")
+
+
+def load_hungarian_assigner(focal_loss_cost_cls):
+    """``HungarianAssigner3D`` (core/bbox/assigners/hungarian_assigner_3d.py:25-145), ``BBox3DL1Cost``
+    (core/bbox/match_costs/match_cost.py:6-28) and ``normalize_bbox`` (core/bbox/util.py:38-57),
+    AST-extracted from the files where they lie and compiled unmodified.  mmdet (un-vendored,
+    un-pinned) supplies four names the class needs: ``BaseAssigner`` (abstract base -> ``object``),
+    ``AssignResult`` (a record -> namedtuple with the same field order), ``build_match_cost`` (a
+    registry lookup -> a 3-entry dict) and ``FocalLossCost`` -- the one with arithmetic in it, passed
+    in by the caller as a restatement of mmdet 2.x's published formula.
+    Returns (HungarianAssigner3D, BBox3DL1Cost, normalize_bbox)."""
+    import ast
+    import collections
+    import numpy as np
+
+    def extract(path, names):
+        tree = ast.parse(open(path).read())
+        body = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+        assert len(body) == len(names), f"reference source changed: {names} not all found in {path}"
+        for n in body:
+            n.decorator_list = []                              # registry / array-converter decorators
+        return ast.Module(body=body, type_ignores=[])
+
+    AssignResult = collections.namedtuple("AssignResult", ["num_gts", "gt_inds", "max_overlaps", "labels"])
+
+    class _IoUCost:                                            # weight 0.0 in every config, never called
+        def __init__(self, weight=0.0, **kw):
+            self.weight = weight
+
+    ns_util = {"torch": torch}
+    exec(compile(extract(os.path.join(REF_BBOX, "util.py"), ["normalize_bbox"]), "util.py", "exec"), ns_util)
+    ns_cost = {"torch": torch}
+    exec(compile(extract(os.path.join(REF_BBOX, "match_costs", "match_cost.py"), ["BBox3DL1Cost"]),
+                 "match_cost.py", "exec"), ns_cost)
+    table = {"FocalLossCost": focal_loss_cost_cls, "BBox3DL1Cost": ns_cost["BBox3DL1Cost"], "IoUCost": _IoUCost}
+
+    def build_match_cost(cfg):
+        cfg = dict(cfg)
+        return table[cfg.pop("type")](**cfg)
+
+    from scipy.optimize import linear_sum_assignment
+    ns = {"torch": torch, "BaseAssigner": object, "AssignResult": AssignResult, "build_match_cost": build_match_cost,
+          "normalize_bbox": ns_util["normalize_bbox"], "linear_sum_assignment": linear_sum_assignment, "np": np}
+    exec(compile(extract(os.path.join(REF_BBOX, "assigners", "hungarian_assigner_3d.py"), ["HungarianAssigner3D"]),
+                 "hungarian_assigner_3d.py", "exec"), ns)
+    return ns["HungarianAssigner3D"], ns_cost["BBox3DL1Cost"], ns_util["normalize_bbox"]

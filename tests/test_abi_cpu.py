@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    src = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("gd4d_xview.h", "gd4d_glue.h", "gd4d_frustum.h"))
+    src = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("gd4d_xview.h", "gd4d_glue.h", "gd4d_frustum.h", "gd4d_assign.h"))
     return re.findall(r"GD4D_API\s+[\w\s\*]+?\b(gd4d_\w+)\s*\(", src)
 
 
@@ -82,6 +82,7 @@ def test_launch_info_and_status_codes():
     assert lib.gd4d_bias_act(a, a, 900, 10, 1, None) == -2                                      # C % 4
     assert lib.gd4d_add_layernorm_bwd(a, None, a, a, a, a, None, a, None, 900, 256, 1, None) == -1   # relu needs beta
     assert lib.gd4d_unpack_nhwc(a, None, 1, 1, 1, 1, None) == -1
+    assert lib.gd4d_match_cost(a, a, a, a, a, 900, 10, 7, 5, 9, 2.0, 0.25, 0.25, 1e-12, None) == -2   # code < 8
     pc = (C.c_float * 6)(*[0.0] * 6)
     assert lib.gd4d_frustum_pe(a, None, None, None, 6, 4, 4, 8, 928.0, 1600.0, 1.0, 0.1, pc, None) == -1
     assert lib.gd4d_frustum_pe(a, None, a, None, 6, 4, 4, 0, 928.0, 1600.0, 1.0, 0.1, pc, None) == -2

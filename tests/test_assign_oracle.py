@@ -1,0 +1,45 @@
+"""Row f3: the CPU restatement of the Hungarian target assignment vs the reference's own
+HungarianAssigner3D / BBox3DL1Cost / normalize_bbox executed unmodified in this container."""
+import pytest
+import torch
+
+from graph_detr4d_b200 import synthetic as syn
+from oracle import assign_oracle as ao, ref_loader
+
+
+def make_case(Q=900, G=37, C=10, seed=0, code=10):
+    g = torch.Generator().manual_seed(seed)
+    cls = torch.randn(Q, C, generator=g) * 2 - 2
+    bbox = torch.randn(Q, code, generator=g)
+    gt = torch.randn(G, 9, generator=g)
+    gt[:, 3:6] = torch.rand(G, 3, generator=g) * 4 + 0.3            # sizes > 0 (log)
+    labels = torch.randint(0, C, (G,), generator=g)
+    return bbox, cls, gt, labels
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs /root/reference")
+@pytest.mark.parametrize("Q,G,seed", [(900, 37, 0), (300, 1, 1), (50, 80, 2), (64, 0, 3)])
+def test_restatement_matches_executed_reference(Q, G, seed):
+    H3D, L1, norm = ref_loader.load_hungarian_assigner(ao.FocalLossCost)
+    assigner = H3D(cls_cost=dict(type="FocalLossCost", weight=2.0), reg_cost=dict(type="BBox3DL1Cost", weight=0.25),
+                   iou_cost=dict(type="IoUCost", weight=0.0), pc_range=syn.PC_RANGE)
+    bbox, cls, gt, labels = make_case(Q, G, seed=seed)
+    res = assigner.assign(bbox, cls, gt, labels)
+    inds, lab = ao.hungarian_assign(bbox, cls, gt, labels)
+    assert res.num_gts == G and torch.equal(res.gt_inds, inds) and torch.equal(res.labels, lab)
+    if G:
+        assert torch.equal(norm(gt, syn.PC_RANGE), ao.normalize_bbox(gt))
+        want = assigner.cls_cost(cls, labels) + assigner.reg_cost(bbox[:, :8], norm(gt, syn.PC_RANGE)[:, :8])
+        assert torch.equal(torch.nan_to_num(want, nan=100.0, posinf=100.0, neginf=-100.0),
+                           ao.match_cost(bbox, cls, gt, labels))
+        assert int((inds > 0).sum()) == min(Q, G)
+
+
+def test_nan_predictions_are_sanitised_like_the_reference():
+    bbox, cls, gt, labels = make_case(40, 5, seed=5)
+    bbox[3, 2] = float("nan")
+    cls[7, :] = float("inf")
+    cost = ao.match_cost(bbox, cls, gt, labels)
+    assert torch.isfinite(cost).all() and float(cost[3].max()) == 100.0
+    inds, _ = ao.hungarian_assign(bbox, cls, gt, labels)
+    assert int((inds > 0).sum()) == 5
