@@ -18,6 +18,7 @@ MAX_LEVELS = 8
 MODE_A, MODE_C, MODE_V2 = 0, 1, 2
 F32, BF16 = 0, 1
 FLAG_TMA_FORWARD = 1
+FLAG_L2_PREFETCH = 2
 
 EXPORTS = (
     "gd4d_abi_version",

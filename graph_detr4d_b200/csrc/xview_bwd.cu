@@ -127,6 +127,7 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
   float* doff = gsum + kMaxLP;                      // dL/d offset (p,3)
   CandB* cands = reinterpret_cast<CandB*>(doff + 3 * kMaxLP);
   const int LP = p.L * p.P;
+  const bool l2_prefetch = (p.flags & GD4D_FLAG_L2_PREFETCH) != 0;
 
   WorkIter wi;
   work_begin(p, wi);
@@ -196,6 +197,22 @@ xview_bwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
             raw[u][1][j] = ldg_nc_v4_all(reinterpret_cast<const char*>(base + o01 + o));
             raw[u][2][j] = ldg_nc_v4_all(reinterpret_cast<const char*>(base + o10 + o));
             raw[u][3][j] = ldg_nc_v4_all(reinterpret_cast<const char*>(base + o11 + o));
+          }
+        }
+        if (l2_prefetch) {  // next batch's corner rows -> L2 while this batch's gathers are in flight
+#pragma unroll
+          for (int u = 0; u < INF; ++u) {
+            const int it = j0 + (INF + u) * GROUPS + grp;
+            if (it < nchunk) {
+              const RecB* r = recs + it;
+              const VT* base = static_cast<const VT*>(p.value[r->meta & 0xff]) + sub * VEC;
+#pragma unroll
+              for (int j = 0; j < NV; ++j) {
+                const int o = j * LANES * VEC;
+                prefetch_l2(base + r->o00 + o); prefetch_l2(base + r->o01 + o);
+                prefetch_l2(base + r->o10 + o); prefetch_l2(base + r->o11 + o);
+              }
+            }
           }
         }
 #pragma unroll

@@ -109,6 +109,12 @@ __device__ __forceinline__ uint4 ldg_nc_v4_all(const char* p) {
   return t;
 }
 
+// L2 prefetch of a row the warp will gather in the NEXT batch: costs no register, so it raises the
+// memory-level parallelism beyond what the register file allows (GD4D_FLAG_L2_PREFETCH).
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ void pin(uint4& a, uint4& b, uint4& c, uint4& d) {
   asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z),
                     "+r"(b.w), "+r"(c.x), "+r"(c.y), "+r"(c.z), "+r"(c.w), "+r"(d.x), "+r"(d.y),

@@ -49,6 +49,7 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
   float* sw = reinterpret_cast<float*>(recs + 32);
   Cand* cands = reinterpret_cast<Cand*>(sw + kMaxLP);
   const int lane_off = sub * 16;      // this lane's 16 bytes inside a (LANES*16)-byte run
+  const bool l2_prefetch = (p.flags & GD4D_FLAG_L2_PREFETCH) != 0;
 
   WorkIter wi;
   work_begin(p, wi);
@@ -80,6 +81,21 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
             raw[u][1][j] = ldg_nc_v4_all(r.p01 + o);
             raw[u][2][j] = ldg_nc_v4_all(r.p10 + o);
             raw[u][3][j] = ldg_nc_v4_all(r.p11 + o);
+          }
+        }
+        if (l2_prefetch) {  // next batch's corner rows -> L2 while this batch's gathers are in flight
+#pragma unroll
+          for (int u = 0; u < INF; ++u) {
+            const int it = j0 + (INF + u) * GROUPS + grp;
+            if (it < nchunk) {
+              const RecF* r = recs + it;
+#pragma unroll
+              for (int j = 0; j < NV; ++j) {
+                const int o = lane_off + j * LANES * 16;
+                prefetch_l2(r->p00 + o); prefetch_l2(r->p01 + o);
+                prefetch_l2(r->p10 + o); prefetch_l2(r->p11 + o);
+              }
+            }
           }
         }
 #pragma unroll

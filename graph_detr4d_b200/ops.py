@@ -7,6 +7,7 @@ CPU / eager fallback: CPU tensors or a missing library raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -22,6 +23,7 @@ __all__ = ["XViewConfig", "GenLayout", "pack_features", "PackedFeatures", "xview
 
 DYNAMIC_SCHEDULE = True   # persistent grid + work counter (False: one warp per item, static)
 TMA_FORWARD = False       # wide forward through the cp.async.bulk staging path (xview_fwd_tma.cu)
+L2_PREFETCH = os.environ.get("GD4D_L2_PREFETCH", "0") != "0"   # prefetch.global.L2 of the next batch's rows
 _LAUNCHES = 0      # kernels of libgd4d_xview.so launched by this process (bench: gpu_launches)
 
 
@@ -297,6 +299,8 @@ def _fill_params(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: in
         p.sched = _sched_ptr(ref.device)
         if TMA_FORWARD and cfg.wide:
             p.flags = _lib.FLAG_TMA_FORWARD
+    if L2_PREFETCH:
+        p.flags |= _lib.FLAG_L2_PREFETCH
     return p
 
 

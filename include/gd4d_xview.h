@@ -64,6 +64,9 @@ typedef enum gd4d_dtype { GD4D_F32 = 0, GD4D_BF16 = 1 } gd4d_dtype;
 /* forward, wide mode, sched set: stage the corner rows in shared memory with TMA bulk
  * copies (cp.async.bulk + mbarrier pipeline) instead of register gathers */
 #define GD4D_FLAG_TMA_FORWARD 1u
+/* forward and backward: prefetch the NEXT batch's corner rows into L2 (prefetch.global.L2) while
+ * the current batch's register gathers are in flight */
+#define GD4D_FLAG_L2_PREFETCH 2u
 
 /*
  * One decoder-layer invocation.  All pointers are device pointers.
