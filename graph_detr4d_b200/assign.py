@@ -15,6 +15,7 @@ Same results as the per-layer reference (tests/test_assign_gpu.py).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -27,6 +28,22 @@ try:
     from scipy.optimize import linear_sum_assignment
 except ImportError:                                            # the reference raises at call time, too (:128-130)
     linear_sum_assignment = None
+
+
+_POOL = None
+
+
+def solve_all(mats):
+    """linear_sum_assignment of every (Q, G) matrix in ``mats``; the L x B independent problems are
+    solved on a small thread pool (scipy's solver releases the GIL: 1.9 -> 1.0 ms for six 900x40
+    problems), results in input order."""
+    global _POOL
+    if len(mats) <= 1:
+        return [linear_sum_assignment(m) for m in mats]
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1)))
+    return list(_POOL.map(linear_sum_assignment, mats))
 
 
 class BatchedHungarianAssigner3D:
@@ -92,15 +109,12 @@ class BatchedHungarianAssigner3D:
         cost_np, lab_np = host.numpy(), lab_host.numpy()
         lab_off = np.concatenate([[0], np.cumsum([g for _, g in layout])])
         flat_idx, gt_idx, gt_lab = [], [], []
-        for b, (off, G) in enumerate(layout):
-            if G == 0:
-                continue
-            mats = cost_np[off:off + L * Q * G].reshape(L, Q, G)
-            for l in range(L):
-                rows, cols = linear_sum_assignment(mats[l])                    # :132
-                flat_idx.append((l * B + b) * Q + rows)
-                gt_idx.append(cols + 1)                                        # :142
-                gt_lab.append(lab_np[lab_off[b] + cols])                       # :143
+        jobs = [(l, b, cost_np[off + l * Q * G:off + (l + 1) * Q * G].reshape(Q, G))
+                for b, (off, G) in enumerate(layout) if G > 0 for l in range(L)]
+        for (l, b, _), (rows, cols) in zip(jobs, solve_all([m for _, _, m in jobs])):   # :132
+            flat_idx.append((l * B + b) * Q + rows)
+            gt_idx.append(cols + 1)                                            # :142
+            gt_lab.append(lab_np[lab_off[b] + cols])                           # :143
         packed = np.stack([np.concatenate(flat_idx), np.concatenate(gt_idx), np.concatenate(gt_lab)]).astype(np.int64)
         m = torch.from_numpy(packed).pin_memory().to(dev, non_blocking=True)   # ONE host -> device copy
         inds.view(-1)[m[0]] = m[1]

@@ -43,3 +43,15 @@ def test_nan_predictions_are_sanitised_like_the_reference():
     assert torch.isfinite(cost).all() and float(cost[3].max()) == 100.0
     inds, _ = ao.hungarian_assign(bbox, cls, gt, labels)
     assert int((inds > 0).sum()) == 5
+
+
+def test_threaded_solver_equals_sequential():
+    """The product's thread-pool solve (host logic, no GPU) returns exactly scipy's sequential results."""
+    import numpy as np
+    from scipy.optimize import linear_sum_assignment
+    from graph_detr4d_b200.assign import solve_all
+    rng = np.random.default_rng(0)
+    mats = [rng.standard_normal((200, g)).astype(np.float32) for g in (40, 1, 13, 250, 40, 7)]
+    for (r1, c1), m in zip(solve_all(mats), mats):
+        r2, c2 = linear_sum_assignment(m)
+        assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
