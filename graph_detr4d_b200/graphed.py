@@ -54,6 +54,7 @@ class GraphedTrainStep:
         self.flat_grad = torch.zeros(n if flat else 1, device=dev, dtype=torch.float32)
         self.flat_views = []
         self._reduce: List[torch.Tensor] = []
+        self._grouped_ok = True
         if flat:
             o = 0
             for p in params:
@@ -118,9 +119,19 @@ class GraphedTrainStep:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
             return
         # ONE grouped NCCL launch (ncclGroupStart/End) over ~20 tensors, in place
-        with dist.distributed_c10d._coalescing_manager():
-            for t in self._reduce:
-                dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        if self._grouped_ok:
+            try:
+                with dist.distributed_c10d._coalescing_manager():
+                    for t in self._reduce:
+                        dist.all_reduce(t, op=dist.ReduceOp.AVG)
+                return
+            except (RuntimeError, ValueError, AttributeError, AssertionError) as e:   # private torch API: degrade, loudly
+                import warnings
+                warnings.warn(f"grouped all-reduce unavailable ({e!r}); falling back to one all-reduce per buffer")
+                self._grouped_ok = False
+                dist.distributed_c10d._world.pg_coalesce_state.pop(dist.distributed_c10d._get_default_group(), None)
+        for t in self._reduce:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
 
     def set_inputs(self, feats: Optional[Sequence[torch.Tensor]] = None, img_metas=None):
         """Stream-ordered refresh of the static inputs (H2D when ``feats`` are host tensors)."""
