@@ -16,7 +16,7 @@ Same results as the per-layer reference (tests/test_assign_gpu.py).
 from __future__ import annotations
 
 import os
-from typing import List, Sequence, Tuple
+from typing import Sequence, Tuple
 
 import numpy as np
 import torch

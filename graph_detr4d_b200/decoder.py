@@ -21,7 +21,7 @@ very same decoder around the oracle's port of the attention.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Sequence
+from typing import Callable, Optional
 
 import torch
 import torch.nn as nn

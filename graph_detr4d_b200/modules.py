@@ -40,7 +40,7 @@ from __future__ import annotations
 import math
 import warnings
 import weakref
-from typing import List, Optional, Sequence, Union
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch

@@ -18,7 +18,7 @@ from typing import Dict, Sequence, Tuple
 
 import torch
 
-from .ops import MODE_A, MODE_C
+from .ops import MODE_C
 
 
 @torch.no_grad()
