@@ -135,3 +135,40 @@ def test_deferred_batched_wgrad_matches_immediate():
     for n in a:
         assert a[n].shape == b[n].shape, n
         assert H.rel_err(b[n], a[n]) <= 1e-4, n
+
+
+def test_training_mode_with_dropout_takes_the_unfused_bias_paths():
+    """dropout = 0.1 in train mode: the bias-deferring shortcuts must step aside (bias before
+    dropout), the generic self-attention path runs, and -- with the same RNG seed, since both
+    variants draw their dropout masks in the same order -- the result equals the eager op chains
+    (fused.ENABLED = False)."""
+    from graph_detr4d_b200 import fused
+    sc = H.scene(B=1, T=1, Q=64)
+    torch.manual_seed(21)
+    cfg = dict(type="Deform3DCrossAttn", num_cams=6, num_points=4, pc_range=syn.PC_RANGE, dropout=0.1)
+    dec = Detr3DTransformerDecoder(cfg, num_layers=2, dropout=0.1)
+    model = Detr3DTransformer(dec, num_query=64)
+    for i, layer in enumerate(dec.layers):
+        syn.randomize_generators(layer.attentions[1], seed=30 + i)
+    model = model.cuda().train()
+    feats = [f.cuda() for f in sc["feats"]]
+    gout = torch.randn(2, 64, 1, 256, generator=torch.Generator().manual_seed(5)).cuda()
+    outs = {}
+    for enabled in (True, False):
+        fused.ENABLED = enabled
+        try:
+            g.clear_caches()
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(1234)
+            fs = [f.clone().requires_grad_(True) for f in feats]
+            st, _, refs = model(fs, sc["metas"], 1)
+            (st * gout).sum().backward()
+            outs[enabled] = (st.detach().clone(), fs[0].grad.clone(),
+                             model.decoder.layers[1].attentions[1].output_proj.bias.grad.clone(),
+                             model.decoder.layers[0].ffns[0].layers[1].bias.grad.clone())
+        finally:
+            fused.ENABLED = True
+    assert torch.isfinite(outs[True][0]).all()
+    assert not torch.equal(outs[True][0], torch.zeros_like(outs[True][0]))
+    for a, b in zip(outs[True], outs[False]):
+        assert H.rel_err(a, b) <= 2e-4
