@@ -20,9 +20,49 @@ class _P(C.Structure):
                 ("out", C.c_void_p), ("mask", C.c_void_p)]
 
 
+LIB_GLUE = os.path.join(HERE, "c", "_build", "libglue_ref.so")
+
+
 def build():
-    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "c")], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "c"), "all"], check=True)
     return LIB
+
+
+def pe_frustum(img2lidar, mask_in, H, W, D, pad_h, pad_w, depth_start, bin_size, pc_range):
+    """oracle/c/glue_ref.c::pe_frustum -> (out (BN,3D,H,W) float32, mask (BN,H,W) uint8)."""
+    if not os.path.exists(LIB_GLUE):
+        build()
+    lib = C.CDLL(LIB_GLUE)
+    m = np.ascontiguousarray(img2lidar, dtype=np.float32).reshape(-1, 16)
+    BN = m.shape[0]
+    mi = None if mask_in is None else np.ascontiguousarray(mask_in, dtype=np.uint8).reshape(BN, H, W)
+    out = np.zeros((BN, 3 * D, H, W), dtype=np.float32)
+    mask = np.zeros((BN, H, W), dtype=np.uint8)
+    lo = (C.c_float * 3)(*[pc_range[i] for i in range(3)])
+    span = (C.c_float * 3)(*[pc_range[3 + i] - pc_range[i] for i in range(3)])
+    lib.pe_frustum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    st = lib.pe_frustum(m.ctypes.data, None if mi is None else mi.ctypes.data, out.ctypes.data, mask.ctypes.data,
+                        BN, H, W, D, pad_h, pad_w, depth_start, bin_size, lo, span)
+    assert st == 0
+    return out, mask
+
+
+def match_cost(cls_pred, bbox_pred, gt, labels, cls_w=2.0, reg_w=0.25, alpha=0.25, eps=1e-12):
+    """oracle/c/glue_ref.c::match_cost -> (Q,G) float32."""
+    if not os.path.exists(LIB_GLUE):
+        build()
+    lib = C.CDLL(LIB_GLUE)
+    cp = np.ascontiguousarray(cls_pred, dtype=np.float32)
+    bp = np.ascontiguousarray(bbox_pred, dtype=np.float32)
+    g = np.ascontiguousarray(gt, dtype=np.float32)
+    lab = np.ascontiguousarray(labels, dtype=np.int64)
+    cost = np.zeros((cp.shape[0], g.shape[0]), dtype=np.float32)
+    lib.match_cost.argtypes = [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_float] * 4
+    st = lib.match_cost(cp.ctypes.data, bp.ctypes.data, g.ctypes.data, lab.ctypes.data, cost.ctypes.data,
+                        cp.shape[0], cp.shape[1], bp.shape[1], g.shape[0], g.shape[1], cls_w, reg_w, alpha, eps)
+    assert st == 0
+    return cost
 
 
 def forward(mode, feats, ref, attn_logits, lidar2img, pc_range, img_h, img_w, num_heads, num_points,
