@@ -342,7 +342,7 @@ def main():
                     config=dict(workload=workload_name(T, dtype), layers=LAYERS, queries=Q, cams=N,
                                 points=POINTS, heads=HEADS, per_gpu_batch=1, optimizer="AdamW (one-launch gd4d_adamw_multi, torch.optim.AdamW arithmetic, device step counter)",
                                 value_proj="fused: gather-then-project (no dense per-pixel GEMM)",
-                                execution="CUDA graphs (fwd+bwd graph, NCCL all-reduce of flat grads if N>1, optimizer graph)",
+                                execution="CUDA graphs (fwd+bwd graph; if N>1 one grouped in-place NCCL all-reduce of the batched gradient buffers; optimizer graph)",
                                 features="NCHW fp32 in, packed channel-last once per step inside the step",
                                 parallelism=f"dp{world}" if world > 1 else "single",
                                 l2="inputs larger than L2 (feature maps + dense grad maps >= 2x126 MB per layer)"),
