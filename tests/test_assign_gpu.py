@@ -56,3 +56,20 @@ def test_assigner_refuses_cpu_tensors():
     bbox, cls, gts, labs = _batch(1, 1, 8, [2])
     with pytest.raises(RuntimeError):
         BatchedHungarianAssigner3D().assign_layers(bbox, cls, gts, labs)
+
+
+def test_batched_assignment_matches_reference_golden():
+    """Same inputs as the [6-1-900] case above, expected outputs frozen from the reference's own
+    HungarianAssigner3D executed in the build container (tests/golden/make_golden_assign.py)."""
+    import os
+    import numpy as np
+    gd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "assign.npz"))
+    bbox, cls = torch.as_tensor(gd["bbox"]).cuda(), torch.as_tensor(gd["cls"]).cuda()
+    gt, labels = torch.as_tensor(gd["gt"]).cuda(), torch.as_tensor(gd["labels"]).cuda()
+    asg = BatchedHungarianAssigner3D()
+    inds, labs = asg.assign_layers(bbox, cls, [gt], [labels])
+    assert torch.equal(inds.cpu(), torch.as_tensor(gd["inds"])) and torch.equal(labs.cpu(), torch.as_tensor(gd["out_labels"]))
+    buf, layout = asg.match_costs(bbox, cls, [gt], [labels])
+    got = buf[:900 * 37].view(900, 37).cpu()
+    want = torch.as_tensor(gd["cost0"])
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())

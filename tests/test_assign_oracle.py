@@ -55,3 +55,17 @@ def test_threaded_solver_equals_sequential():
     for (r1, c1), m in zip(solve_all(mats), mats):
         r2, c2 = linear_sum_assignment(m)
         assert np.array_equal(r1, r2) and np.array_equal(c1, c2)
+
+
+def test_oracle_reproduces_reference_golden():
+    """tests/golden/assign.npz = the reference's own HungarianAssigner3D executed in the build container."""
+    import os
+    import numpy as np
+    gd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "assign.npz"))
+    gt, labels = torch.as_tensor(gd["gt"]), torch.as_tensor(gd["labels"])
+    for l in range(gd["bbox"].shape[0]):
+        bbox, cls = torch.as_tensor(gd["bbox"][l, 0]), torch.as_tensor(gd["cls"][l, 0])
+        inds, lab = ao.hungarian_assign(bbox, cls, gt, labels)
+        assert torch.equal(inds, torch.as_tensor(gd["inds"][l, 0])) and torch.equal(lab, torch.as_tensor(gd["out_labels"][l, 0]))
+    assert torch.equal(ao.match_cost(torch.as_tensor(gd["bbox"][0, 0]), torch.as_tensor(gd["cls"][0, 0]), gt, labels),
+                       torch.as_tensor(gd["cost0"]))
