@@ -67,6 +67,13 @@ class BatchedHungarianAssigner3D:
         bp = all_bbox_preds.detach().float().permute(1, 0, 2, 3).reshape(B, L * Q, code).contiguous()
         cp = all_cls_scores.detach().float().permute(1, 0, 2, 3).reshape(B, L * Q, Ccls).contiguous()
         sizes = [int(g.shape[0]) for g in gt_bboxes_list]
+        if len(gt_bboxes_list) != B or len(gt_labels_list) != B:
+            raise ValueError(f"need one gt box / label tensor per sample (B={B})")
+        for b, (gb, gl) in enumerate(zip(gt_bboxes_list, gt_labels_list)):
+            if gl.numel() != sizes[b]:
+                raise ValueError(f"sample {b}: {gl.numel()} labels for {sizes[b]} gt boxes")
+            if sizes[b] and (gb.dim() != 2 or gb.shape[1] < 7):
+                raise ValueError(f"sample {b}: gt boxes must be (G, >=7), got {tuple(gb.shape)}")
         offs = np.concatenate([[0], np.cumsum([L * Q * g for g in sizes])]).astype(np.int64)
         buf = torch.empty(int(offs[-1]), device=bp.device, dtype=torch.float32)
         lib = _lib.load()
@@ -107,6 +114,11 @@ class BatchedHungarianAssigner3D:
         lab_host.copy_(lab_dev, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         cost_np, lab_np = host.numpy(), lab_host.numpy()
+        num_classes = int(all_cls_scores.shape[-1])
+        if lab_np.size and (lab_np.min() < 0 or lab_np.max() >= num_classes):
+            # the kernel wrote cost 100 for those columns instead of reading out of bounds
+            raise ValueError(f"gt label outside [0, {num_classes}): ignore / background labels must be filtered "
+                             f"before assignment (got min {lab_np.min()}, max {lab_np.max()})")
         lab_off = np.concatenate([[0], np.cumsum([g for _, g in layout])])
         flat_idx, gt_idx, gt_lab = [], [], []
         jobs = [(l, b, cost_np[off + l * Q * G:off + (l + 1) * Q * G].reshape(Q, G))

@@ -27,6 +27,10 @@ match_cost_kernel(const float* __restrict__ cls_pred, const float* __restrict__ 
 #pragma unroll
   for (int k = 0; k < 8; ++k) reg += fabsf(p[k] - n[k]);                       // torch.cdist(p=1)
   const int64_t lab = labels[g];
+  if (lab < 0 || lab >= C) {   // ignore / background label: never index cls_pred out of bounds; the host
+    cost[i] = 100.f;           // side (assign.py) rejects such labels after its one sync
+    return;
+  }
   const float x = cls_pred[static_cast<size_t>(row) * C + lab];
   const float s = __fdiv_rn(1.f, 1.f + expf(-x));                              // sigmoid
   const float neg = -logf((1.f - s) + eps) * (1.f - alpha) * (s * s);

@@ -95,14 +95,17 @@ __device__ __forceinline__ RecB build_record_bwd(const gd4d_xview_params& p, con
   const int slot = (MODE == GD4D_MODE_C) ? (l * p.P + pi) : 0;  // softmax slot (<= 63); unused in mode A
   r.meta = static_cast<int>((active ? 0x80000000u : 0u) | (static_cast<unsigned>(k) << 16) |
                             (static_cast<unsigned>(slot) << 8) | static_cast<unsigned>(l));
-  const int x0 = min(max(f.x0, 0), W - 1), x1 = min(max(f.x0 + 1, 0), W - 1);
-  const int y0 = min(max(f.y0, 0), H - 1), y1 = min(max(f.y0 + 1, 0), H - 1);
+  const int x0 = f.x0, x1 = f.x0 + 1, y0 = f.y0, y1 = f.y0 + 1;
   const long long img = static_cast<long long>(w.b) * p.N + n;
   const long long base = img * H * W * p.C + (WIDE ? 0 : w.h * kHeadDim);
-  r.o00 = base + (static_cast<long long>(y0) * W + x0) * p.C;
-  r.o01 = base + (static_cast<long long>(y0) * W + x1) * p.C;
-  r.o10 = base + (static_cast<long long>(y1) * W + x0) * p.C;
-  r.o11 = base + (static_cast<long long>(y1) * W + x1) * p.C;
+  // out-of-map corners (all coefficients 0, REDs skipped) and padding records gather the zero row
+  // (xview_common.cuh) -- its element offset from this level's base; both are 16-byte aligned
+  const long long z = (reinterpret_cast<const char*>(g_zero_row) - static_cast<const char*>(p.value[l])) /
+                      static_cast<long long>(sizeof(VT));
+  r.o00 = (active && f.in00) ? base + (static_cast<long long>(y0) * W + x0) * p.C : z;
+  r.o01 = (active && f.in01) ? base + (static_cast<long long>(y0) * W + x1) * p.C : z;
+  r.o10 = (active && f.in10) ? base + (static_cast<long long>(y1) * W + x0) * p.C : z;
+  r.o11 = (active && f.in11) ? base + (static_cast<long long>(y1) * W + x1) * p.C : z;
   return r;
 }
 

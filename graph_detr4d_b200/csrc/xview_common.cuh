@@ -22,6 +22,18 @@ constexpr int kHeadDim = 32;       // channels per head slice (C / Hh)
 constexpr int kMaxLP = 64;         // L*P logits per head kept in shared memory
 constexpr float kEps = 1e-5f;
 
+// 2 KB of zeros.  Out-of-map bilinear corners and padding records of the branch-free gathers point
+// here instead of at a clamped in-map pixel: the reference's zeros padding (F.grid_sample, mmcv MSDA)
+// never READS a pixel outside the map, and weight 0 times a non-finite border pixel would be NaN.
+static __device__ __align__(16) unsigned char g_zero_row[2048];
+
+// torch.nan_to_num (detr3d_transformer.py:378, :619): NaN -> 0, +-Inf -> +-FLT_MAX
+__device__ __forceinline__ float nan_to_num_(float x) {
+  if (x != x) return 0.f;
+  if (fabsf(x) == INFINITY) return copysignf(3.402823466e+38f, x);
+  return x;
+}
+
 struct Projected {
   float u, v;      // normalised image coords (divided by the unpadded image size)
   float cx, cy;    // camera-plane numerators   (backward only)

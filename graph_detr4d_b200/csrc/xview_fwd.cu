@@ -64,16 +64,20 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     float wsum_lane = 0.f;
     const int total = nvalid * p.L;
     for (int c0 = 0; c0 < total; c0 += 32) {
-      recs[lane] = build_record<MODE, VT, WIDE>(p, cands, sw, c0 + lane, total, w, wsum_lane);
+      float wt_item;
+      recs[lane] = build_record<MODE, VT, WIDE>(p, cands, sw, c0 + lane, total, w, wsum_lane, wt_item);
+      if (MODE != GD4D_MODE_C) sw[lane] = wt_item;   // mode A: applied AFTER nan_to_num(sample); sw is free (no softmax)
       __syncwarp();
       const int nchunk = min(32, total - c0);
       for (int j0 = 0; j0 < nchunk; j0 += INF * GROUPS) {
         uint4 raw[INF][4][NV];
         float wgt[INF][4];
+        float wtA[INF];
 #pragma unroll
         for (int u = 0; u < INF; ++u) {
           const RecF r = recs[j0 + u * GROUPS + grp];
           wgt[u][0] = r.w00; wgt[u][1] = r.w01; wgt[u][2] = r.w10; wgt[u][3] = r.w11;
+          wtA[u] = (MODE != GD4D_MODE_C) ? sw[j0 + u * GROUPS + grp] : 0.f;
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
             const int o = lane_off + j * LANES * 16;
@@ -113,12 +117,20 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
             Slice<VT>::unpack(raw[u][3][j], c11);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-              float a = acc[j * VEC + i];
-              a = fmaf(wgt[u][0], c00[i], a);
-              a = fmaf(wgt[u][1], c01[i], a);
-              a = fmaf(wgt[u][2], c10[i], a);
-              a = fmaf(wgt[u][3], c11[i], a);
-              acc[j * VEC + i] = a;
+              if (MODE == GD4D_MODE_C) {
+                float a = acc[j * VEC + i];
+                a = fmaf(wgt[u][0], c00[i], a);
+                a = fmaf(wgt[u][1], c01[i], a);
+                a = fmaf(wgt[u][2], c10[i], a);
+                a = fmaf(wgt[u][3], c11[i], a);
+                acc[j * VEC + i] = a;
+              } else {  // detr3d_transformer.py:378: nan_to_num on the bilinear sample, then the weight
+                float sm = wgt[u][0] * c00[i];
+                sm = fmaf(wgt[u][1], c01[i], sm);
+                sm = fmaf(wgt[u][2], c10[i], sm);
+                sm = fmaf(wgt[u][3], c11[i], sm);
+                acc[j * VEC + i] = fmaf(wtA[u], nan_to_num_(sm), acc[j * VEC + i]);
+              }
             }
           }
       }

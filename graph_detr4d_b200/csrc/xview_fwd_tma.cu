@@ -87,7 +87,8 @@ xview_fwd_tma_kernel(const __grid_constant__ gd4d_xview_params p, const int cand
     float wsum_lane = 0.f;
     const int total = nvalid * p.L;
     for (int c0 = 0; c0 < total; c0 += 32) {
-      recs[lane] = build_record<MODE, VT, true>(p, cands, sw, c0 + lane, total, w, wsum_lane);
+      float wt_item;
+      recs[lane] = build_record<MODE, VT, true>(p, cands, sw, c0 + lane, total, w, wsum_lane, wt_item);
       __syncwarp();
       const int nchunk = min(32, total - c0);
       const int nb = (nchunk + B - 1) / B;

@@ -22,13 +22,13 @@ struct __align__(16) RecF {
   const char* p01;
   const char* p10;
   const char* p11;
-  float w00, w01, w10, w11;  // bilinear weight * attention weight; 0 when out of the map
-};
+  float w00, w01, w10, w11;  // mode C: bilinear weight * attention weight; mode A: bilinear weight only
+};                           // (the sample passes through nan_to_num before its weight); 0 when out of the map
 
 template <int MODE, typename VT, bool WIDE>
 __device__ __forceinline__ RecF build_record(const gd4d_xview_params& p, const Cand* cands,
                                              const float* sw, int item, int total, const WarpCtx& w,
-                                             float& wsum_lane) {
+                                             float& wsum_lane, float& wt_out) {
   RecF r;
   const bool active = item < total;
   const int it = active ? item : 0;
@@ -54,20 +54,26 @@ __device__ __forceinline__ RecF build_record(const gd4d_xview_params& p, const C
   const float b10 = (1.f - f.tx) * f.ty, b11 = f.tx * f.ty;
   const float i00 = f.in00 ? b00 : 0.f, i01 = f.in01 ? b01 : 0.f;
   const float i10 = f.in10 ? b10 : 0.f, i11 = f.in11 ? b11 : 0.f;
-  r.w00 = wt * i00; r.w01 = wt * i01; r.w10 = wt * i10; r.w11 = wt * i11;
+  wt_out = wt;
+  if (MODE == GD4D_MODE_C) {
+    r.w00 = wt * i00; r.w01 = wt * i01; r.w10 = wt * i10; r.w11 = wt * i11;
+  } else {
+    r.w00 = i00; r.w01 = i01; r.w10 = i10; r.w11 = i11;
+  }
   wsum_lane = fmaf(wt, (i00 + i01) + (i10 + i11), wsum_lane);
-  // clamped corner coordinates: always a valid address, weight is already 0 if outside
-  const int x0 = min(max(f.x0, 0), W - 1), x1 = min(max(f.x0 + 1, 0), W - 1);
-  const int y0 = min(max(f.y0, 0), H - 1), y1 = min(max(f.y0 + 1, 0), H - 1);
+  const int x0 = f.x0, x1 = f.x0 + 1, y0 = f.y0, y1 = f.y0 + 1;
   const size_t img = static_cast<size_t>(w.b) * p.N + n;
   const size_t rowb = static_cast<size_t>(p.C) * sizeof(VT);
   const char* base = static_cast<const char*>(p.value[l]) + img * H * W * rowb +
                      (WIDE ? 0 : static_cast<size_t>(w.h) * kHeadDim * sizeof(VT));
   const size_t r0 = static_cast<size_t>(y0) * W, r1 = static_cast<size_t>(y1) * W;
-  r.p00 = base + (r0 + x0) * rowb;
-  r.p01 = base + (r0 + x1) * rowb;
-  r.p10 = base + (r1 + x0) * rowb;
-  r.p11 = base + (r1 + x1) * rowb;
+  // out-of-map corners (weight 0) and padding records gather the zero row: always a valid address,
+  // never a pixel the reference would not read
+  const char* z = reinterpret_cast<const char*>(g_zero_row);
+  r.p00 = (active && f.in00) ? base + (r0 + x0) * rowb : z;
+  r.p01 = (active && f.in01) ? base + (r0 + x1) * rowb : z;
+  r.p10 = (active && f.in10) ? base + (r1 + x0) * rowb : z;
+  r.p11 = (active && f.in11) ? base + (r1 + x1) * rowb : z;
   return r;
 }
 

@@ -134,7 +134,7 @@ xview_v2_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap)
         if (!BWD) {
 #pragma unroll
           for (int i = 0; i < VEC; ++i)
-            acc[i] = fmaf(wt, w00 * c00[i] + w01 * c01[i] + w10 * c10[i] + w11 * c11[i], acc[i]);
+            acc[i] = fmaf(wt, nan_to_num_(w00 * c00[i] + w01 * c01[i] + w10 * c10[i] + w11 * c11[i]), acc[i]);  // :619
         } else {
           float* gv = p.grad_value[it.l];
           if (gv != nullptr && wt != 0.f) {

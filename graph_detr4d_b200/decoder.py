@@ -31,6 +31,15 @@ from .glue import can_defer_bias, fast_layer_norm, fast_linear, linear_relu, sel
 from .modules import build_attention, inverse_sigmoid
 
 
+# In-place refresh of the packed generator weights (one multi-tensor copy per forward instead of two
+# concatenations per layer).  The packed copy is what the generator GEMM saves for its backward, so an
+# in-place refresh is only safe when every forward is followed by its backward before the next forward
+# -- which the CUDA-graph step (graphed.GraphedTrainStep) guarantees and sets this flag for.  Eager
+# callers (two forwards before one backward: teacher/student, multi-sample losses) get a fresh
+# concatenation per forward, like the reference's three separate Linears.
+STATIC_GENERATOR_PACKS = False
+
+
 def _dropout_active(m: nn.Module) -> bool:
     return isinstance(m, nn.Dropout) and m.training and m.p > 0
 
@@ -158,6 +167,8 @@ class Detr3DTransformerDecoder(nn.Module):
         concatenations per layer."""
         if not (fused.ENABLED and query.is_cuda and query.dtype == torch.float32):
             return
+        if not (STATIC_GENERATOR_PACKS or torch.cuda.is_current_stream_capturing()):
+            return
         dsts, srcs, mods = [], [], []
         for layer in self.layers:
             m = layer.attentions[1]
@@ -195,6 +206,10 @@ class Detr3DTransformerDecoder(nn.Module):
             if self.return_intermediate:
                 intermediate.append(output)
                 intermediate_ref.append(reference_points)
+        # the per-forward pack of the feature maps has served all layers: drop the cache's strong
+        # references (autograd keeps what backward needs), so one step's maps do not outlive it
+        from . import modules as _modules
+        _modules.clear_pack_cache()
         if self.return_intermediate:
             return torch.stack(intermediate), torch.stack(intermediate_ref)
         return output, reference_points

@@ -463,6 +463,6 @@ def self_attention(query, query_pos, mha: torch.nn.MultiheadAttention, out_bias:
     k = k.reshape(L, B * H, d).transpose(0, 1)
     v = v.reshape(L, B * H, d).transpose(0, 1)
     attn = _ScaledBmmNT.apply(q, k, 1.0 / math.sqrt(d)).softmax(-1)
-    attn = torch.nn.functional.dropout(attn, mha.dropout)
+    attn = torch.nn.functional.dropout(attn, mha.dropout, training=mha.training)   # eval: identity
     out = torch.bmm(attn, v).transpose(0, 1).reshape(L, B, E)
     return fast_linear(out, mha.out_proj, add_bias=out_bias)

@@ -23,6 +23,7 @@ from typing import Callable, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
+from . import decoder as _decoder
 from . import modules
 from .glue import DeferredWgrad
 from .optim import MultiTensorAdamW
@@ -70,6 +71,7 @@ class GraphedTrainStep:
         self._forward_loss = forward_loss
 
         def fwd_bwd():
+            _decoder.STATIC_GENERATOR_PACKS = True         # forward and backward alternate strictly here
             modules.clear_pack_cache()                     # the pack kernels must be part of the capture
             for p in params:
                 p.grad = None
@@ -90,6 +92,7 @@ class GraphedTrainStep:
                     torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
                     for v, p in zip(self.flat_views, params):
                         p.grad = v                         # the optimizer reads the (all-reduced) flat views
+            _decoder.STATIC_GENERATOR_PACKS = False
             return loss.detach()
 
         side = torch.cuda.Stream(device=dev)

@@ -24,7 +24,10 @@ Differences from the reference, all deliberate:
   * Deform3DCrossAttn with batch size > 1: the reference's ``query.repeat(N,1,1)``
     (deform3d_cross_attn.py:277) pairs attention logits of sample ``i % B`` with
     image ``i = b*N+n``; that is only self-consistent for B == 1 (every config uses
-    samples_per_gpu=1).  Here sample b always uses its own logits.
+    samples_per_gpu=1).  The module therefore RAISES for B > 1 (as Detr3DCrossAttenV2 does),
+    unless built with ``allow_batched=True`` (new key), in which case every sample uses its
+    own logits -- NOT what the reference computes for B > 1 (the oracle reproduces the
+    reference's pairing and is pinned to it: tests/test_oracle_vs_reference.py).
   * ``feature_dtype='bf16'`` (new): keep the packed / value-projected maps in bf16
     (fp32 accumulation in the kernel).
   * Deform3DCrossAttn ``value_proj_mode`` (new): ``'fused'`` (default) never runs
@@ -158,17 +161,24 @@ class _PackCache:
         self._refs = None
         self._versions = None
         self._dtype = None
+        self._grad = None
         self._packed = None
+
+    @staticmethod
+    def _grad_state(value):
+        # a pack made under no_grad has no gradient sink: it must not serve a later training forward
+        return (torch.is_grad_enabled(), tuple(bool(v.requires_grad) for v in value))
 
     def get(self, value: Sequence[torch.Tensor], dtype) -> PackedFeatures:
         if self._refs is not None and len(self._refs) == len(value) and self._dtype == dtype and \
                 all(r() is v for r, v in zip(self._refs, value)) and \
-                self._versions == [v._version for v in value]:
+                self._versions == [v._version for v in value] and self._grad == self._grad_state(value):
             return self._packed
         packed = ops.pack_features(value, dtype)
         self._refs = [weakref.ref(v) for v in value]
         self._versions = [v._version for v in value]
         self._dtype = dtype
+        self._grad = self._grad_state(value)
         self._packed = packed
         return packed
 
@@ -181,6 +191,8 @@ class _Lidar2ImgCache:
     only when the matrices change: hoists the reference's per-layer list->numpy->tensor
     H2D copy (detr3d_transformer.py:398-402) to once per distinct sample, and gives
     CUDA-graph replays a static address to read."""
+
+    static = False          # set by lidar2img_device(): keep ONE address (graph capture), refresh in place
 
     def __init__(self):
         self._arr = None
@@ -196,8 +208,13 @@ class _Lidar2ImgCache:
                     raise RuntimeError("lidar2img changed during CUDA-graph capture; call "
                                        "lidar2img_device(img_metas, device) before capturing")
                 self._arr = arr
-                with torch.no_grad():
-                    self._tensor.copy_(torch.from_numpy(arr))
+                if self.static or not torch.is_grad_enabled():
+                    with torch.no_grad():                      # CUDA-graph replays read this address
+                        self._tensor.copy_(torch.from_numpy(arr))
+                else:
+                    # an earlier forward may have saved the old tensor for its backward (two forwards
+                    # before one backward: teacher/student, multi-sample losses): never overwrite it
+                    self._tensor = torch.from_numpy(arr).to(device)
             return self._tensor
         self._arr, self._key = arr, key
         self._tensor = torch.from_numpy(arr).to(device)
@@ -215,10 +232,13 @@ def clear_pack_cache():
 def clear_caches():
     _PACK_CACHE.clear()
     _L2I_CACHE.__init__()
+    _L2I_CACHE.static = False
 
 
 def lidar2img_device(img_metas, device) -> torch.Tensor:
-    """Upload / refresh the static lidar2img buffer (call outside CUDA-graph capture)."""
+    """Upload / refresh the STATIC lidar2img buffer (call outside CUDA-graph capture): from now on the
+    buffer keeps its address and is refreshed in place, which is what graph replays need."""
+    _L2I_CACHE.static = True
     return _L2I_CACHE.get(img_metas, device)
 
 
@@ -468,11 +488,12 @@ class Deform3DCrossAttn(BaseModule):
     def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=5, num_cams=6,
                  im2col_step=64, pc_range=None, dropout=0.1, norm_cfg=None, init_cfg=None,
                  batch_first=False, fix_offset=False, depth_encode=False, feature_dtype=None,
-                 value_proj_mode="fused"):
+                 value_proj_mode="fused", allow_batched=False):
         super().__init__(init_cfg)
         if value_proj_mode not in ("fused", "dense"):
             raise ValueError("value_proj_mode must be 'fused' or 'dense'")
         self.value_proj_mode = value_proj_mode
+        self.allow_batched = bool(allow_batched)
         if embed_dims % num_heads != 0:
             raise ValueError(f"embed_dims must be divisible by num_heads, "
                              f"but got {embed_dims} and {num_heads}")
@@ -593,6 +614,12 @@ class Deform3DCrossAttn(BaseModule):
         if packed.N != self.num_cams or len(packed.levels) != self.num_levels:
             raise ValueError(f"expected {self.num_cams} cams x {self.num_levels} levels, got "
                              f"{packed.N} x {len(packed.levels)}")
+        if packed.B != 1 and not self.allow_batched:
+            raise ValueError(
+                "Deform3DCrossAttn: batch size > 1.  The reference pairs image b*N+n with the attention "
+                "logits of sample (b*N+n) % B (query.repeat(N,1,1), deform3d_cross_attn.py:277), which is "
+                "only self-consistent for B == 1 (all configs use samples_per_gpu=1).  Build the module "
+                "with allow_batched=True to give every sample its own logits instead.")
         img_h, img_w = _img_hw(img_metas)
         l2i = _L2I_CACHE.get(img_metas, query.device)
         # The three generator Linears read the same query: on the CUDA fp32 path they are ONE GEMM over

@@ -149,7 +149,7 @@ def msda_pytorch(value, spatial_shapes, sampling_locations, attention_weights):
 
 
 def xview_c_core(values, reference_points, offsets, attn_logits, cam_logits, lidar2img,
-                 pc_range, img_h, img_w, num_heads):
+                 pc_range, img_h, img_w, num_heads, reference_batch_order=False):
     """What one variant-C kernel launch computes (deform3d_cross_attn.py:211-324
     minus the Linears).
 
@@ -158,6 +158,12 @@ def xview_c_core(values, reference_points, offsets, attn_logits, cam_logits, lid
     attn_logits : (B,Q,Hh*L*P) raw attention_weights output (softmax over L*P)
     cam_logits  : (B,Q,N) raw cam_attention_weights output (the reference VIEWS it
                   as (B,N,Q,1): quirk A.4-1, reproduced here)
+    reference_batch_order : for B > 1 the reference pairs image i = b*N+n with the attention
+                  logits of sample i % B (``query.repeat(N,1,1)``, :277, against cam-fastest
+                  locations, :274 -- quirk A.4-2).  True reproduces exactly that (pinned against the
+                  executed reference in tests/test_oracle_vs_reference.py); False gives every sample
+                  its own logits (what the product computes when ``allow_batched=True``).  Identical
+                  for B == 1.
     Returns out (B,Q,C) and the per-point mask (B,N,Q,Hh,L,P) bool."""
     B, Q = reference_points.shape[:2]
     N = lidar2img.size(1)
@@ -179,7 +185,10 @@ def xview_c_core(values, reference_points, offsets, attn_logits, cam_logits, lid
     value = flat.view(B * N, -1, Hh, C // Hh)                               # :280
     # :277,281-282 -- query.repeat(N,1,1): with the b-fastest batch order only B==1 is
     # self-consistent; the restatement indexes (b,n) consistently with locs (cam-fastest).
-    aw = attn_logits.view(B, 1, Q, Hh, L * P).expand(B, N, Q, Hh, L * P).reshape(B * N, Q, Hh, L * P)
+    if reference_batch_order:
+        aw = attn_logits.view(B, Q, Hh, L * P).repeat(N, 1, 1, 1)          # row i <- sample i % B
+    else:
+        aw = attn_logits.view(B, 1, Q, Hh, L * P).expand(B, N, Q, Hh, L * P).reshape(B * N, Q, Hh, L * P)
     m = mask.view(B * N, Q, Hh, L * P)                                      # :283
     aw = aw.softmax(-1) * m                                                 # :284
     out = msda_pytorch(value, shapes, locs, aw.view(B * N, Q, Hh, L, P))    # :301-309
@@ -188,7 +197,7 @@ def xview_c_core(values, reference_points, offsets, attn_logits, cam_logits, lid
 
 
 def xview_c_wide_core(feats, reference_points, offsets, attn_logits, cam_logits, lidar2img,
-                      pc_range, img_h, img_w, num_heads):
+                      pc_range, img_h, img_w, num_heads, return_mask=False):
     """Gather-then-project restatement: every head samples ALL C raw channels with its
     own points/weights.  Built from ``xview_c_core`` itself (features repeated once per
     head, so head h's "slice" is the whole map) -- no new arithmetic.
@@ -198,12 +207,13 @@ def xview_c_wide_core(feats, reference_points, offsets, attn_logits, cam_logits,
     B, Q = reference_points.shape[:2]
     C = feats[0].shape[2]
     rep = [f.repeat(1, 1, num_heads, 1, 1) for f in feats]
-    agg, _ = xview_c_core(rep, reference_points, offsets, attn_logits, cam_logits, lidar2img,
-                          pc_range, img_h, img_w, num_heads)
+    agg, mask = xview_c_core(rep, reference_points, offsets, attn_logits, cam_logits, lidar2img,
+                             pc_range, img_h, img_w, num_heads)
     ones = [torch.ones_like(f[:, :, :1]).repeat(1, 1, num_heads, 1, 1) for f in feats]
     wsum, _ = xview_c_core(ones, reference_points, offsets, attn_logits, cam_logits, lidar2img,
                            pc_range, img_h, img_w, num_heads)
-    return agg.view(B, Q, num_heads, C).transpose(1, 2), wsum.view(B, Q, num_heads).transpose(1, 2)
+    agg, wsum = agg.view(B, Q, num_heads, C).transpose(1, 2), wsum.view(B, Q, num_heads).transpose(1, 2)
+    return (agg, wsum, mask) if return_mask else (agg, wsum)
 
 
 # --------------------------------------------------------------------------
@@ -307,7 +317,7 @@ def detr3d_cross_atten_v2_forward(sd, query, value, query_pos, reference_points,
 
 
 def deform3d_cross_attn_forward(sd, query, value, query_pos, reference_points, img_metas,
-                                pc_range, num_heads, depth_encode=False):
+                                pc_range, num_heads, depth_encode=False, reference_batch_order=False):
     """Deform3DCrossAttn.forward, eval mode (deform3d_cross_attn.py:152-339)."""
     inp_residual = query
     q = (query + query_pos).permute(1, 0, 2)
@@ -322,7 +332,7 @@ def deform3d_cross_attn_forward(sd, query, value, query_pos, reference_points, i
         vv = _lin(sd, "value_proj", v.reshape(B * N, C, H * W).transpose(1, 2))
         proj.append(vv.transpose(1, 2).reshape(B, N, C, H, W))
     out, _ = xview_c_core(proj, reference_points, offsets, logits, cam_logits, l2i,
-                          pc_range, img_h, img_w, num_heads)
+                          pc_range, img_h, img_w, num_heads, reference_batch_order=reference_batch_order)
     out = _lin(sd, "output_proj", out).permute(1, 0, 2)
     r3d = reference_points.clone()
     if depth_encode:

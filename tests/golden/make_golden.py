@@ -6,6 +6,10 @@ representable, half the bytes), the reference module's state_dict, its eval-mode
 forward output and the gradients of sum(out * gout) w.r.t. query, reference
 points and every feature level.  Small on purpose (embed_dims=64 -> 2 heads of
 32 channels) so the fixtures stay a few hundred KB.
+
+Variant "C256" is Deform3DCrossAttn at the REAL width (embed_dims=256, 8 heads, 6 cameras) on tiny
+maps (8x12 .. 1x2): with 1 KB pixel rows the product takes its default "wide" (gather-then-project)
+kernels -- the ones bench.py times -- so a reference-held fixture pins that path too.
 """
 import contextlib
 import io
@@ -30,9 +34,14 @@ def bf16_bits(t):
 
 
 def run(variant):
+    global C, HEADS, Q, SHAPES
     ref = ref_loader.load()
     T = 2 if variant == "C" else 1
     N = 6 * T
+    if variant == "C256":
+        C, HEADS, Q, SHAPES = 256, 8, 64, [(8, 12), (4, 6), (2, 3), (1, 2)]
+    else:
+        C, HEADS, Q, SHAPES = 64, 2, 48, [(12, 20), (6, 10), (3, 5), (2, 3)]
     feats = [f.to(torch.bfloat16).float() for f in syn.make_feats(1, N, C, SHAPES, seed=11)]
     query, query_pos, rp = syn.make_queries(1, Q, C, seed=12)
     metas = syn.make_img_metas(1, T)
@@ -57,6 +66,7 @@ def run(variant):
     (out * gout).sum().backward()
     data = dict(
         variant=np.array(variant), num_frames=np.array(T), shapes=np.array(SHAPES),
+        embed_dims=np.array(C), num_heads=np.array(HEADS),
         query=query.detach().numpy(), query_pos=query_pos.numpy(), ref=rp.detach().numpy(),
         gout=gout.numpy(), out=out.detach().numpy(),
         grad_query=query.grad.numpy(), grad_ref=rp.grad.numpy(),
@@ -78,6 +88,6 @@ def run(variant):
 if __name__ == "__main__":
     import warnings
     warnings.filterwarnings("ignore")
-    only = sys.argv[1:] or ["A", "C", "V2"]
+    only = sys.argv[1:] or ["A", "C", "V2", "C256"]
     for v in only:
         run(v)

@@ -80,9 +80,36 @@ def test_lidar2img_cache_reuses_upload_only_for_equal_matrices():
     b = c.get(syn.make_img_metas(1, 1), torch.device("cpu"))
     assert a is b and a.dtype == torch.float32 and tuple(a.shape) == (1, 6, 4, 4)
     metas[0]["lidar2img"][0] = metas[0]["lidar2img"][0] * 2
+    old = a.clone()
     a2 = c.get(metas, torch.device("cpu"))
-    assert a2 is a                                        # same static buffer, refreshed in place
+    # autograd may be recording: an earlier forward can have SAVED the old tensor for its backward
+    # (two forwards before one backward), so changed matrices get a NEW tensor, the old one is intact
+    assert a2 is not a and torch.equal(a, old)
     assert torch.equal(a2[0, 0], torch.as_tensor(metas[0]["lidar2img"][0].astype(np.float32)))
+    # static mode (CUDA-graph replays read a fixed address) and no_grad: refreshed in place
+    c.static = True
+    metas[0]["lidar2img"][1] = metas[0]["lidar2img"][1] * 3
+    a3 = c.get(metas, torch.device("cpu"))
+    assert a3 is a2 and torch.equal(a3[0, 1], torch.as_tensor(metas[0]["lidar2img"][1].astype(np.float32)))
+    c.static = False
+    with torch.no_grad():
+        metas[0]["lidar2img"][2] = metas[0]["lidar2img"][2] * 5
+        assert c.get(metas, torch.device("cpu")) is a2
+
+
+def test_pack_cache_key_includes_grad_state():
+    """A pack made under no_grad has no gradient sink; it must not be served to a later training
+    forward on the same (static) feature tensors."""
+    assert modules._PackCache._grad_state([torch.zeros(1, requires_grad=True)]) == (True, (True,))
+    with torch.no_grad():
+        assert modules._PackCache._grad_state([torch.zeros(1, requires_grad=True)]) == (False, (True,))
+
+
+def test_deform3d_refuses_batches_unless_allowed():
+    import graph_detr4d_b200 as g
+    m = g.Deform3DCrossAttn(num_cams=6, num_points=4, pc_range=syn.PC_RANGE)
+    assert m.allow_batched is False
+    assert g.Deform3DCrossAttn(num_cams=6, num_points=4, pc_range=syn.PC_RANGE, allow_batched=True).allow_batched
 
 
 def test_synthetic_rig_valid_fraction():

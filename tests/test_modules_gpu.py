@@ -13,12 +13,14 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("variant,cls", [("A", "Detr3DCrossAtten"), ("C", "Deform3DCrossAttn"),
-                                         ("V2", "Detr3DCrossAttenV2")])
+                                         ("V2", "Detr3DCrossAttenV2"), ("C256", "Deform3DCrossAttn")])
 def test_module_matches_reference_golden(variant, cls):
+    """Outputs and gradients frozen from the UNMODIFIED reference classes (tests/golden/make_golden.py).
+    "C256" has 1 KB pixel rows, so the module runs its default wide (gather-then-project) kernels."""
     gd = load_golden(variant)
     N = 6 * gd["T"]
-    m = getattr(g, cls)(embed_dims=64, num_heads=2, num_levels=4, num_points=1 if variant == "A" else 4,
-                        num_cams=N, pc_range=syn.PC_RANGE).cuda().eval()
+    m = getattr(g, cls)(embed_dims=gd["C"], num_heads=gd["heads"], num_levels=4,
+                        num_points=1 if variant == "A" else 4, num_cams=N, pc_range=syn.PC_RANGE).cuda().eval()
     m.load_state_dict(gd["sd"], strict=True)
     feats = [f.cuda().requires_grad_(True) for f in gd["feats"]]
     q = gd["query"].cuda().requires_grad_(True)
@@ -27,6 +29,8 @@ def test_module_matches_reference_golden(variant, cls):
     y = m(q, None, feats, query_pos=gd["query_pos"].cuda(), reference_points=rp, img_metas=gd["metas"])
     (y * gd["gout"].cuda()).sum().backward()
     assert tuple(y.shape) == tuple(gd["out"].shape)
+    if variant == "C256":
+        assert m._use_wide(g.ops.pack_features([f.detach() for f in feats]))
     assert H.rel_err(y.detach().cpu(), gd["out"]) <= 1e-5
     assert H.rel_err(q.grad.cpu(), gd["grad_query"]) <= 2e-4
     assert H.rel_err(rp.grad.cpu(), gd["grad_ref"]) <= 2e-4

@@ -28,12 +28,14 @@ def load_golden(variant):
     l2i = z["lidar2img"]
     metas = [dict(lidar2img=[l2i[n] for n in range(l2i.shape[0])], img_shape=[syn.IMG_SHAPE] * l2i.shape[0])]
     t = lambda k: torch.from_numpy(z[k].copy())
-    return dict(z=z, T=T, feats=feats, sd=sd, metas=metas, query=t("query"), query_pos=t("query_pos"),
+    C = int(z["embed_dims"]) if "embed_dims" in z else 64        # A / C / V2 fixtures predate the key
+    heads = int(z["num_heads"]) if "num_heads" in z else 2
+    return dict(z=z, T=T, C=C, heads=heads, feats=feats, sd=sd, metas=metas, query=t("query"), query_pos=t("query_pos"),
                 ref=t("ref"), gout=t("gout"), out=t("out"), grad_query=t("grad_query"), grad_ref=t("grad_ref"),
                 grad_feats=[t(f"grad_feat{j}") for j in range(i)])
 
 
-@pytest.mark.parametrize("variant", ["A", "C", "V2"])
+@pytest.mark.parametrize("variant", ["A", "C", "V2", "C256"])
 def test_oracle_reproduces_golden(variant):
     gd = load_golden(variant)
     feats = [f.clone().requires_grad_(True) for f in gd["feats"]]
@@ -46,7 +48,7 @@ def test_oracle_reproduces_golden(variant):
                                              syn.PC_RANGE, num_heads=2)
     else:
         y = xo.deform3d_cross_attn_forward(gd["sd"], q, feats, gd["query_pos"], rp, gd["metas"],
-                                           syn.PC_RANGE, num_heads=2)
+                                           syn.PC_RANGE, num_heads=gd["heads"])
     (y * gd["gout"]).sum().backward()
     assert H.rel_err(y.detach(), gd["out"]) <= 2e-6
     assert H.rel_err(q.grad, gd["grad_query"]) <= 1e-5

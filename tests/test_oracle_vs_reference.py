@@ -96,6 +96,24 @@ def test_variant_c_module(ref, T, P):
         assert H.rel_err(a.grad, b.grad) <= 1e-5
 
 
+def test_variant_c_module_batch2_reference_batch_order(ref):
+    """B > 1 (quirk A.4-2): ``query.repeat(N,1,1)`` (deform3d_cross_attn.py:277) pairs image
+    i = b*N+n with the attention logits of sample i % B.  The oracle reproduces exactly that with
+    ``reference_batch_order=True`` and differs from it with per-sample logits -- which is why the
+    product refuses B > 1 unless ``allow_batched=True``."""
+    sc = H.scene(B=2, T=1, Q=60)
+    torch.manual_seed(6)
+    mod = ref.Deform3DCrossAttnCPU(num_cams=sc["N"], num_points=4, pc_range=syn.PC_RANGE).eval()
+    syn.randomize_generators(mod)
+    y_ref = _quiet(mod, sc["query"], None, sc["feats"], query_pos=sc["query_pos"], reference_points=sc["ref"],
+                   img_metas=sc["metas"])
+    args = (mod.state_dict(), sc["query"], sc["feats"], sc["query_pos"], sc["ref"], sc["metas"], syn.PC_RANGE, 8)
+    y_quirk = xo.deform3d_cross_attn_forward(*args, reference_batch_order=True)
+    y_sane = xo.deform3d_cross_attn_forward(*args, reference_batch_order=False)
+    assert H.rel_err(y_quirk, y_ref) <= 2e-6
+    assert H.rel_err(y_sane, y_ref) > 1e-3
+
+
 def test_variant_v2_module(ref):
     sc = H.scene(B=1, T=1, Q=90)
     torch.manual_seed(5)
