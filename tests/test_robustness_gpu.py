@@ -133,8 +133,11 @@ def test_non_finite_pixels_outside_the_footprint_do_not_leak(mode, wide):
     fin_o, fin_k = torch.isfinite(want), torch.isfinite(out)
     # never MORE non-finite outputs than the reference semantics produce
     assert not (fin_o & ~fin_k).any(), int((fin_o & ~fin_k).sum())
-    ok = fin_o & fin_k & (want.abs() < 1e30)                    # (the reference also turns masked-out points that
-    assert ok.float().mean() > 0.5                               #  touch a poisoned pixel into NaN: 0 * Inf; we skip them)
+    # (the reference ALSO turns every masked-out point that touches a poisoned pixel into NaN -- 0 * Inf:
+    # it samples first and masks after -- so most of its outputs are NaN here; the kernel never samples
+    # masked-out points.  Compare where both are finite.)
+    ok = fin_o & fin_k & (want.abs() < 1e30)
+    assert int(ok.sum()) > 2000
     assert H.rel_err(out[ok], want[ok]) <= 1e-5
 
 
