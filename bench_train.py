@@ -105,30 +105,12 @@ class Detector(nn.Module):
         return states, refs, cls, reg
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=2)
-    args = ap.parse_args()
-    sys.stdout.flush()
-    real_stdout = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+def run_train(world, rank, local_rank, dev, T=2, steps=10, warmup=3):
+    """Time the end-to-end training step; returns the result dict on rank 0 (None elsewhere).
+    The caller owns process-group setup (bench.py calls this as one of its extra legs)."""
     torch.backends.cudnn.benchmark = True
     from graph_detr4d_b200 import _lib, ops, synthetic as syn
     _lib.load(build_if_missing=False)
-
-    T = args.frames
     N = 6 * T
     torch.manual_seed(0)
     model = Detector(N).to(dev).train()
@@ -159,13 +141,13 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     calls0 = ops.launch_count()
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step()
     e.record()
     barrier()
@@ -174,16 +156,46 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    line = None
     if rank == 0:
-        line = dict(metric="train_frames_per_s", value=world * args.steps / (ms * 1e-3), unit="frames/s",
-                    n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
+        line = dict(metric="train_frames_per_s", value=world * steps / (ms * 1e-3), unit="frames/s",
+                    n_gpus=world, steps=steps, warmup=max(warmup, 3), ms_per_step=ms / steps,
                     higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16 backbone+FPN (autocast) / f32 decoder", data="synthetic",
                     config=dict(workload=f"graph_detr4d_e2e_train_T{T}_N{N}_928x1600_res50_fpn_dec6_Q900",
                                 per_gpu_batch=1, parallelism=f"ddp{world}", loss="synthetic (no Hungarian)",
-                                features="FPN emits channels_last -> fused kernels read zero-copy"),
+                                features="FPN emits channels_last -> fused kernels read zero-copy",
+                                h2d_bytes_per_step=img_host.numel() * 4),
                     gpu_launches=(ops.launch_count() - calls0), final_loss=float(loss),
                     peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
+    del net, model, opt, img_host
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=2)
+    args = ap.parse_args()
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    line = run_train(world, rank, local_rank, dev, T=args.frames, steps=args.steps, warmup=args.warmup)
+    if rank == 0:
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if world > 1:

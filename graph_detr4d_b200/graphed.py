@@ -32,6 +32,34 @@ MULTI_TENSOR_ADAMW = os.environ.get("GD4D_MULTI_ADAMW", "1") != "0"      # A/B s
 COALESCED_ALLREDUCE = os.environ.get("GD4D_COALESCED_ALLREDUCE", "1") != "0"
 
 
+class HostFeatureBuffer:
+    """The feature maps of one step in ONE pinned host allocation (``views`` are the per-level
+    (B,N,C,H,W) tensors inside it), so that a step's host->device transfer is a single
+    ``cudaMemcpyAsync`` instead of one per level."""
+
+    def __init__(self, shapes: Sequence[Sequence[int]], dtype: torch.dtype = torch.float32):
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        self.flat = torch.empty(sum(sizes), dtype=dtype).pin_memory()
+        self.views, o = [], 0
+        for s, n in zip(shapes, sizes):
+            self.views.append(self.flat[o:o + n].view(*s))
+            o += n
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+
+def _flat_like(feats: Sequence[torch.Tensor]):
+    """One device allocation holding copies of ``feats`` back to back -> (flat, per-tensor views)."""
+    flat = torch.empty(sum(f.numel() for f in feats), device=feats[0].device, dtype=feats[0].dtype)
+    views, o = [], 0
+    for f in feats:
+        views.append(flat[o:o + f.numel()].view(f.shape))
+        o += f.numel()
+    return flat, views
+
+
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, forward_loss: Callable[[Sequence[torch.Tensor]], torch.Tensor],
                  example_feats: Sequence[torch.Tensor], img_metas, lr=2e-4, weight_decay=0.01,
@@ -64,8 +92,18 @@ class GraphedTrainStep:
         # one-launch AdamW over all parameter tensors (optim.py); torch.optim.AdamW arithmetic
         self.opt = (MultiTensorAdamW(params, lr=lr, weight_decay=weight_decay) if MULTI_TENSOR_ADAMW else
                     torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=True, capturable=True))
-        self.static_feats: List[torch.Tensor] = [
-            f.detach().clone().requires_grad_(feats_require_grad) for f in example_feats]
+        # the static inputs of the captured step live back to back in ONE allocation, so a new step's
+        # maps arrive with one copy (host->device or device->device) instead of one per level
+        same = len({f.dtype for f in example_feats}) == 1
+        if same:
+            self._static_flat, views = _flat_like(example_feats)
+            with torch.no_grad():
+                for v, f in zip(views, example_feats):
+                    v.copy_(f)
+            self.static_feats: List[torch.Tensor] = [v.requires_grad_(feats_require_grad) for v in views]
+        else:
+            self._static_flat = None
+            self.static_feats = [f.detach().clone().requires_grad_(feats_require_grad) for f in example_feats]
         self.img_metas = img_metas
         modules.lidar2img_device(img_metas, dev)           # upload once, outside capture
         self._forward_loss = forward_loss
@@ -146,25 +184,41 @@ class GraphedTrainStep:
                     dst.copy_(src, non_blocking=True)
 
     # ---- host-buffer pipeline: H2D of step i+1 overlaps the compute of step i ------------
-    def prefetch(self, feats_host: Sequence[torch.Tensor]):
-        """Start the H2D copy of the NEXT step's (pinned) feature maps on a copy stream."""
+    def prefetch(self, feats_host):
+        """Start the H2D copy of the NEXT step's (pinned) feature maps on a copy stream.
+        ``feats_host``: a ``HostFeatureBuffer`` (ONE copy) or a sequence of pinned tensors (one per level)."""
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._staging = [torch.empty_like(f) for f in self.static_feats]
+            if self._static_flat is not None:
+                self._staging_flat, self._staging = _flat_like([f.detach() for f in self.static_feats])
+            else:
+                self._staging_flat, self._staging = None, [torch.empty_like(f) for f in self.static_feats]
             self._staged = torch.cuda.Event()
             self._consumed = torch.cuda.Event()
             self._consumed.record(torch.cuda.current_stream(self.device))
         self._copy_stream.wait_event(self._consumed)        # staging is free again
         with torch.cuda.stream(self._copy_stream), torch.no_grad():
-            for dst, src in zip(self._staging, feats_host):
-                dst.copy_(src, non_blocking=True)
+            if isinstance(feats_host, HostFeatureBuffer) and self._staging_flat is not None and \
+                    feats_host.flat.dtype == self._staging_flat.dtype and \
+                    feats_host.flat.numel() == self._staging_flat.numel():
+                self._staging_flat.copy_(feats_host.flat, non_blocking=True)      # ONE cudaMemcpyAsync
+            else:
+                srcs = feats_host.views if isinstance(feats_host, HostFeatureBuffer) else feats_host
+                for dst, src in zip(self._staging, srcs):
+                    dst.copy_(src, non_blocking=True)
             self._staged.record(self._copy_stream)
 
     def commit(self, img_metas=None):
         """Make the prefetched maps the inputs of the next ``step()`` (one D2D copy)."""
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._staged)
-        self.set_inputs(self._staging, img_metas)
+        if self._staging_flat is not None:
+            if img_metas is not None:
+                modules.lidar2img_device(img_metas, self.device)
+            with torch.no_grad():
+                self._static_flat.copy_(self._staging_flat, non_blocking=True)    # one D2D for all levels
+        else:
+            self.set_inputs(self._staging, img_metas)
         self._consumed.record(cur)
 
     def step(self) -> torch.Tensor:
