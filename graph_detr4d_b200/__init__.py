@@ -9,9 +9,11 @@ from .modules import (ATTENTION, Deform3DCrossAttn, Detr3DCrossAtten, Detr3DCros
                       clear_caches, inverse_sigmoid, lidar2img_device)
 from .ops import (MODE_A, MODE_C, PackedFeatures, XViewConfig, pack_features,  # noqa: F401
                   xview_attention, xview_backward, xview_forward)
-from . import assign, fused, frustum, optim  # noqa: F401,E402   (rows f2-f4 of SURVEY 8f)
+from . import assign, fpe, fused, frustum, loss_sync, optim  # noqa: F401,E402   (rows f2-f4 of SURVEY 8f)
 from .assign import BatchedHungarianAssigner3D  # noqa: F401,E402
 from .frustum import position_embeding  # noqa: F401,E402
+from .fpe import position_embed_features  # noqa: F401,E402
+from .loss_sync import packed_avg_factors  # noqa: F401,E402
 from .optim import MultiTensorAdamW  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -42,6 +42,11 @@ EXPORTS = (
     "gd4d_frustum_pe",
     # include/gd4d_assign.h
     "gd4d_match_cost",
+    # include/gd4d_fpe.h
+    "gd4d_level_mask",
+    "gd4d_sine_pe3d",
+    "gd4d_fpe_combine_fwd",
+    "gd4d_fpe_combine_bwd",
 )
 
 
@@ -140,7 +145,11 @@ def load(build_if_missing: bool = True):
                 ("gd4d_adamw_multi", [vp, vp, i32, vp, f32, f32, f32, f32, f32, vp]),
                 ("gd4d_frustum_pe", [vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32,
                                      C.POINTER(C.c_float), vp]),
-                ("gd4d_match_cost", [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, f32, f32, vp])):
+                ("gd4d_match_cost", [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, f32, f32, vp]),
+                ("gd4d_level_mask", [vp, vp, i32, i32, i32, i32, i32, vp]),
+                ("gd4d_sine_pe3d", [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp]),
+                ("gd4d_fpe_combine_fwd", [vp, vp, vp, vp, vp, i64, vp]),
+                ("gd4d_fpe_combine_bwd", [vp, vp, vp, vp, vp, i64, vp])):
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = C.c_int, args
         lib.gd4d_params_size.restype = C.c_int

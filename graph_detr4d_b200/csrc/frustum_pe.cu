@@ -6,6 +6,16 @@
 // applies inverse_sigmoid and writes the (B*N, D*3, H, W) convolution input directly:
 // consecutive threads own consecutive pixels, so every store instruction of a warp is one
 // contiguous 128-byte line of one (d, c) plane.  HBM-write-bound: 12 B per (pixel, depth bin).
+//
+// r2: the r1 kernel spent ~45 instructions per coordinate (two IEEE divisions with their slow-path
+// checks and an accurate logf) and ran at 0.17 of the HBM copy peak, issue-bound.  The MASK needs the
+// reference's exact arithmetic, the VALUE does not (the reference's own BLAS-ordered mat-vec already
+// moves it by ~1e-6 in the normalised domain, tests/test_pe_oracle.py): so
+//   * the out-of-range test is decided on t = acc - lo without dividing: for span > 0,
+//     fl(t / span) > 1  <=>  t > span   (t = nextafter(span) divides to 1 + 2^-23/m, m in [1,2): rounds up)
+//     fl(t / span) < 0  <=>  t < 0      (except when the quotient underflows to -0: that rare case takes
+//                                        the exact division)
+//   * the value uses t * (1/span), MUFU.RCP and MUFU.LG2 (abs. error ~1e-7 in the normalised domain).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -20,7 +30,7 @@ struct FrustumArgs {
   uint8_t* mask_out;
   int H, W, D;
   float pad_h, pad_w, depth_start, bin_size;
-  float lo[3], span[3];
+  float lo[3], span[3], rspan[3];
 };
 
 __global__ void __launch_bounds__(128) frustum_pe_kernel(const FrustumArgs a) {
@@ -48,11 +58,14 @@ __global__ void __launch_bounds__(128) frustum_pe_kernel(const FrustumArgs a) {
       acc = __fadd_rn(acc, __fmul_rn(M[4 * r + 1], py));
       acc = __fadd_rn(acc, __fmul_rn(M[4 * r + 2], z));
       acc = __fadd_rn(acc, M[4 * r + 3]);
-      const float c = __fdiv_rn(__fsub_rn(acc, a.lo[r]), a.span[r]);                                 // :469-474
-      outside += (c > 1.0f) | (c < 0.0f);                                                            // :476
+      const float t = __fsub_rn(acc, a.lo[r]);                                                       // :469-474
+      bool neg = t < 0.f;
+      if (neg && t > -1e-30f) neg = __fdiv_rn(t, a.span[r]) < 0.f;   // quotient may underflow to -0: exact path
+      outside += (t > a.span[r]) | neg;                              // == (c > 1.0) | (c < 0.0), c = fl(t/span)  :476
+      const float c = t * a.rspan[r];
       const float xc = fminf(fmaxf(c, 0.f), 1.f);                                                    // :480
-      const float x1 = fmaxf(xc, eps), x2 = fmaxf(__fsub_rn(1.f, xc), eps);
-      o[static_cast<size_t>(d * 3 + r) * HW] = logf(__fdiv_rn(x1, x2));
+      const float x1 = fmaxf(xc, eps), x2 = fmaxf(1.f - xc, eps);
+      o[static_cast<size_t>(d * 3 + r) * HW] = __logf(__fdividef(x1, x2));
     }
   }
   if (a.mask_out != nullptr) {
@@ -75,7 +88,11 @@ extern "C" int gd4d_frustum_pe(const float* img2lidar, const uint8_t* mask_in, f
   a.img2lidar = img2lidar; a.mask_in = mask_in; a.out = out; a.mask_out = mask_out;
   a.H = H; a.W = W; a.D = D;
   a.pad_h = pad_h; a.pad_w = pad_w; a.depth_start = depth_start; a.bin_size = bin_size;
-  for (int i = 0; i < 3; ++i) { a.lo[i] = pc_lo_span[i]; a.span[i] = pc_lo_span[3 + i]; }
+  for (int i = 0; i < 3; ++i) {
+    a.lo[i] = pc_lo_span[i]; a.span[i] = pc_lo_span[3 + i];
+    if (!(a.span[i] > 0.f)) return GD4D_ERR_DIMS;     // the division-free range test needs span > 0
+    a.rspan[i] = 1.0f / a.span[i];
+  }
   dim3 grid((H * W + 127) / 128, BN);
   gd4d::frustum_pe_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);
   return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;

@@ -273,6 +273,83 @@ def load_position_embeding():
     return ns["position_embeding"]
 
 
+REF_POS_ENC = os.path.join(REF_ROOT, "projects", "mmdet3d_plugin", "models", "utils", "positional_encoding.py")
+
+
+def load_fpe_block():
+    """The feature position-embedding block of ``Detr3DHeadPE.forward``
+    (dense_heads/detr3d_head_pe.py:510-553), executed from the reference's own source:
+
+      * ``forward`` is AST-extracted and CUT right before ``query_embeds = ...`` (:556, the transformer
+        call and the branches are not part of row f4); a ``return mlvl_feats, masks`` is appended.
+        Nothing inside the kept statements is touched.
+      * ``SELayer`` (:231-243) and ``SinePositionalEncoding3D`` (models/utils/positional_encoding.py:15-112)
+        are AST-extracted class definitions, compiled unmodified with ``BaseModule`` bound to
+        ``torch.nn.Module``-with-init_cfg (the shim of this file) and the registry decorator dropped.
+      * ``position_embeding`` is the method loaded by ``load_position_embeding``.
+
+    Returns a namespace with ``forward_fpe(self, mlvl_feats, img_metas)``, ``SELayer``,
+    ``SinePositionalEncoding3D`` and ``position_embeding``; ``make_head`` builds the stub ``self`` with the
+    sub-modules the reference constructs at :386-396."""
+    import ast
+    import math
+    import types
+    import numpy as np
+    import torch.nn as nn
+    import torch.nn.functional as F
+    install_shims()
+    ns = {"np": np, "torch": torch, "nn": nn, "F": F, "math": math, "BaseModule": _BaseModule}
+    tree = ast.parse(open(REF_HEAD_PE).read())
+    fwd = se = None
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "SELayer":
+            se = node
+        if isinstance(node, ast.ClassDef) and node.name == "Detr3DHeadPE":
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name == "forward":
+                    fwd = item
+    assert fwd is not None and se is not None, "reference source changed"
+    keep = []
+    for st in fwd.body:
+        seg = ast.get_source_segment(open(REF_HEAD_PE).read(), st) or ""
+        if seg.startswith("query_embeds"):
+            break
+        keep.append(st)
+    assert len(keep) < len(fwd.body), "cut point (query_embeds = ...) not found"
+    ret = ast.parse("return mlvl_feats, masks").body[0]
+    fwd.body = keep + [ret]
+    fwd.name = "forward_fpe"
+    fwd.decorator_list = []
+    exec(compile(ast.fix_missing_locations(ast.Module(body=[se, fwd], type_ignores=[])), REF_HEAD_PE, "exec"), ns)
+    tree2 = ast.parse(open(REF_POS_ENC).read())
+    pe = next(n for n in tree2.body if isinstance(n, ast.ClassDef) and n.name == "SinePositionalEncoding3D")
+    pe.decorator_list = []
+    exec(compile(ast.Module(body=[pe], type_ignores=[]), REF_POS_ENC, "exec"), ns)
+    ns["position_embeding"] = load_position_embeding()
+
+    def make_head(embed_dims=256, depth_num=64, depth_start=1, pc_range=None, with_detach=True, num_feats=128,
+                  seed=0):
+        torch.manual_seed(seed)
+        head = nn.Module()
+        head.embed_dims, head.depth_num, head.depth_start = embed_dims, depth_num, depth_start
+        head.pc_range, head.with_detach = pc_range, with_detach
+        head.position_dim = 3 * depth_num
+        head.position_encoder = nn.Sequential(                                     # :386-390
+            nn.Conv2d(head.position_dim, embed_dims * 4, kernel_size=1, stride=1, padding=0), nn.ReLU(),
+            nn.Conv2d(embed_dims * 4, embed_dims, kernel_size=1, stride=1, padding=0))
+        head.adapt_pos3d = nn.Sequential(                                          # :391-395
+            nn.Conv2d(embed_dims * 3 // 2, embed_dims * 4, kernel_size=1, stride=1, padding=0), nn.ReLU(),
+            nn.Conv2d(embed_dims * 4, embed_dims, kernel_size=1, stride=1, padding=0))
+        head.fpe = ns["SELayer"](embed_dims)                                       # :396
+        head.positional_encoding = ns["SinePositionalEncoding3D"](num_feats=num_feats, normalize=True, offset=-0.5)
+        head.position_embeding = types.MethodType(ns["position_embeding"], head)
+        return head
+
+    ns["make_head"] = make_head
+    return types.SimpleNamespace(**{k: ns[k] for k in ("forward_fpe", "SELayer", "SinePositionalEncoding3D",
+                                                      "position_embeding", "make_head")})
+
+
 # ------------------------------------------------------------------------------------------
 # HungarianAssigner3D (SURVEY 8f row f3): the reference's own class, executed unmodified
 # ------------------------------------------------------------------------------------------

@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    src = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("gd4d_xview.h", "gd4d_glue.h", "gd4d_frustum.h", "gd4d_assign.h"))
+    inc = os.path.join(ROOT, "include")
+    src = "".join(open(os.path.join(inc, h)).read() for h in sorted(os.listdir(inc)) if h.endswith(".h"))
     return re.findall(r"GD4D_API\s+[\w\s\*]+?\b(gd4d_\w+)\s*\(", src)
 
 
