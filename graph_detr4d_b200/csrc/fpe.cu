@@ -81,12 +81,25 @@ __global__ void __launch_bounds__(128) sine_pe3d_kernel(const int32_t* __restric
   }
   float* o = out + (static_cast<size_t>(b * N + n) * 3 * F) * HW + pix;
   const float e3[3] = {en, ey, ex};                         // cat((pos_n, pos_y, pos_x)) :99
+  // stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=4).view(B,N,H,W,-1) on the 5-D p stacks BEFORE the
+  // feature axis (:90-98): channels [0, F/2) are sin(p[2j]), channels [F/2, F) are cos(p[2j+1]) -- two
+  // halves, not the interleaving the 4-D mmdet original produces.
+  const int Fh = F >> 1;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     float* ok = o + static_cast<size_t>(k) * F * HW;
-    for (int i = 0; i < F; ++i) {
-      const float a = __fdiv_rn(e3[k], s_dim[i]);           // :85-87
-      ok[static_cast<size_t>(i) * HW] = (i & 1) ? cosf(a) : sinf(a);   // stack(sin(0::2), cos(1::2)) :90-98
+    for (int j = 0; j < Fh; ++j) {
+      const float d0 = s_dim[2 * j], d1 = s_dim[2 * j + 1];
+      const float a0 = __fdiv_rn(e3[k], d0);                // :85-87
+      float sn, cs;
+      if (d0 == d1) {
+        sincosf(a0, &sn, &cs);
+      } else {
+        sn = sinf(a0);
+        cs = cosf(__fdiv_rn(e3[k], d1));
+      }
+      ok[static_cast<size_t>(j) * HW] = sn;
+      ok[static_cast<size_t>(Fh + j) * HW] = cs;
     }
   }
 }
@@ -147,7 +160,7 @@ int gd4d_sine_pe3d(const int32_t* img_hw, const float* dim_t, float* out, int32_
                    float offset, void* cuda_stream) {
   if (img_hw == nullptr || dim_t == nullptr || out == nullptr) return GD4D_ERR_NULL;
   if (B <= 0 || B > 65535 || N <= 0 || N > gd4d::kMaxCams || H <= 0 || W <= 0 || pad_h <= 0 || pad_w <= 0 ||
-      F <= 0 || F > 4096)
+      F <= 0 || F > 4096 || (F & 1))          // odd num_feats cannot be stacked in the reference either
     return GD4D_ERR_DIMS;
   dim3 grid((H * W + 127) / 128, N, B);
   gd4d::sine_pe3d_kernel<<<grid, 128, F * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(

@@ -15,9 +15,15 @@
 //     fl(t / span) > 1  <=>  t > span   (t = nextafter(span) divides to 1 + 2^-23/m, m in [1,2): rounds up)
 //     fl(t / span) < 0  <=>  t < 0      (except when the quotient underflows to -0: that rare case takes
 //                                        the exact division)
-//   * the value uses t * (1/span), MUFU.RCP and MUFU.LG2 (abs. error ~1e-7 in the normalised domain).
+//   * the value needs c = fl(t / span) itself: the logit amplifies one ulp of c by 1/(1-c) (up to 1e5 at
+//     the clamp), so t * (1/span) alone is NOT enough (measured 1.8e-3 off).  With r = RN(1/span) from the
+//     host, q = RN(t*r), e = fma(-q, span, t) (exact), c = RN(q + e*r) is the correctly rounded quotient
+//     (Markstein; holds unless span's significand is all ones, which the host entry refuses) -- 3 FP32
+//     ops instead of the ~10-instruction IEEE division with its slow-path check.  The final
+//     log(x1/x2) uses MUFU.RCP/MUFU.LG2 (relative error ~3e-7 on the ratio -> ~3e-7 absolute on the logit).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/gd4d_frustum.h"
 
@@ -62,7 +68,9 @@ __global__ void __launch_bounds__(128) frustum_pe_kernel(const FrustumArgs a) {
       bool neg = t < 0.f;
       if (neg && t > -1e-30f) neg = __fdiv_rn(t, a.span[r]) < 0.f;   // quotient may underflow to -0: exact path
       outside += (t > a.span[r]) | neg;                              // == (c > 1.0) | (c < 0.0), c = fl(t/span)  :476
-      const float c = t * a.rspan[r];
+      const float q = __fmul_rn(t, a.rspan[r]);
+      float c = __fmaf_rn(__fmaf_rn(-q, a.span[r], t), a.rspan[r], q);                              // == fl(t / span)
+      if (!(fabsf(q) < 1e30f)) c = q;                              // inf / nan projections: no inf - inf in the correction
       const float xc = fminf(fmaxf(c, 0.f), 1.f);                                                    // :480
       const float x1 = fmaxf(xc, eps), x2 = fmaxf(1.f - xc, eps);
       o[static_cast<size_t>(d * 3 + r) * HW] = __logf(__fdividef(x1, x2));
@@ -91,7 +99,10 @@ extern "C" int gd4d_frustum_pe(const float* img2lidar, const uint8_t* mask_in, f
   for (int i = 0; i < 3; ++i) {
     a.lo[i] = pc_lo_span[i]; a.span[i] = pc_lo_span[3 + i];
     if (!(a.span[i] > 0.f)) return GD4D_ERR_DIMS;     // the division-free range test needs span > 0
-    a.rspan[i] = 1.0f / a.span[i];
+    uint32_t bits;
+    memcpy(&bits, &a.span[i], 4);
+    if ((bits & 0x7fffffu) == 0x7fffffu) return GD4D_ERR_DIMS;   // Markstein's correction needs a non-all-ones significand
+    a.rspan[i] = static_cast<float>(1.0 / static_cast<double>(a.span[i]));
   }
   dim3 grid((H * W + 127) / 128, BN);
   gd4d::frustum_pe_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(a);

@@ -12,6 +12,9 @@ What is loaded (reference file:line):
   * ``feature_sampling``                 detr3d_transformer.py:397-438
   * ``Detr3DCrossAtten``                 detr3d_transformer.py:229-390
   * ``Detr3DCrossAttenV2``               detr3d_transformer.py:441-709
+  * ``Detr3DTransformerDecoder``         detr3d_transformer.py:151-225   (its mmcv parent is the shim
+        ``TransformerLayerSequence``: an nn.Module with an empty ``layers`` list the test fills)
+  * ``Detr3DTransformer``                detr3d_transformer.py:45-147
   * ``Deform3DCrossAttn``                deform3d_cross_attn.py:33-339
         The shipped non-CUDA branch (deform3d_cross_attn.py:305-309) raises
         NameError (``sampling_locations`` is undefined).  ``variant="cpu"``
@@ -166,7 +169,8 @@ def install_shims():
     _mod("mmcv.cnn.bricks.transformer",
          MultiScaleDeformableAttention=MultiScaleDeformableAttention,
          TransformerLayerSequence=TransformerLayerSequence,
-         build_transformer_layer_sequence=lambda cfg, *a, **k: None)
+         # mmcv builds the sequence from a config dict; the pin hands over an already-built module
+         build_transformer_layer_sequence=lambda cfg, *a, **k: cfg if isinstance(cfg, nn.Module) else None)
     _mod("mmcv.runner")
     _mod("mmcv.runner.base_module", BaseModule=_BaseModule)
     _mod("mmcv.ops")
@@ -235,6 +239,8 @@ def load():
         inverse_sigmoid=dt.inverse_sigmoid,
         Detr3DCrossAtten=dt.Detr3DCrossAtten,
         Detr3DCrossAttenV2=dt.Detr3DCrossAttenV2,
+        Detr3DTransformerDecoder=dt.Detr3DTransformerDecoder,      # detr3d_transformer.py:151-225 (row a9)
+        Detr3DTransformer=dt.Detr3DTransformer,                    # detr3d_transformer.py:45-147
         Deform3DCrossAttn=dc.Deform3DCrossAttn,
         Deform3DCrossAttnCPU=dc_cpu.Deform3DCrossAttn,
         msda_pytorch=_msda_pytorch,
