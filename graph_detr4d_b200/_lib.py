@@ -40,6 +40,7 @@ EXPORTS = (
     "gd4d_adamw_multi",
     # include/gd4d_frustum.h
     "gd4d_frustum_pe",
+    "gd4d_frustum_pe_levels",
     # include/gd4d_assign.h
     "gd4d_match_cost",
     # include/gd4d_fpe.h
@@ -145,6 +146,8 @@ def load(build_if_missing: bool = True):
                 ("gd4d_adamw_multi", [vp, vp, i32, vp, f32, f32, f32, f32, f32, vp]),
                 ("gd4d_frustum_pe", [vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32,
                                      C.POINTER(C.c_float), vp]),
+                ("gd4d_frustum_pe_levels", [vp, vp, vp, vp, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i32,
+                                            f32, f32, f32, f32, C.POINTER(C.c_float), vp]),
                 ("gd4d_match_cost", [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, f32, f32, vp]),
                 ("gd4d_level_mask", [vp, vp, i32, i32, i32, i32, i32, vp]),
                 ("gd4d_sine_pe3d", [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp]),

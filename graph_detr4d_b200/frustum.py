@@ -31,7 +31,7 @@ def frustum_position_input(level_shapes: Sequence[Tuple[int, int]], img_metas, d
                            pc_range, masks: Optional[Sequence[torch.Tensor]] = None, device="cuda",
                            img2lidar: Optional[torch.Tensor] = None):
     """-> ([x_l (B*N, 3*depth_num, H_l, W_l) fp32], [mask_l (B,N,H_l,W_l) bool]): the input of
-    ``position_encoder`` (:486) and ``coords_masks`` (:489), one launch per level."""
+    ``position_encoder`` (:486) and ``coords_masks`` (:489), ONE launch for all levels."""
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("frustum_position_input runs on CUDA only (the CPU oracle lives in oracle/, test-only)")
@@ -48,6 +48,7 @@ def frustum_position_input(level_shapes: Sequence[Tuple[int, int]], img_metas, d
     lib = _lib.load()
     xs: List[torch.Tensor] = []
     ms: List[torch.Tensor] = []
+    m_ins = []
     for lvl, (H, W) in enumerate(level_shapes):
         H, W = int(H), int(W)
         m_in = None
@@ -56,15 +57,21 @@ def frustum_position_input(level_shapes: Sequence[Tuple[int, int]], img_metas, d
             if tuple(m_in.shape) != (B, N, H, W) or not m_in.is_cuda:
                 raise ValueError(f"masks[{lvl}] must be a CUDA (B,N,H,W)=({B},{N},{H},{W}) tensor")
             m_in = m_in.to(torch.uint8).contiguous()
-        out = torch.empty((B * N, 3 * D, H, W), device=device, dtype=torch.float32)
-        m_out = torch.empty((B, N, H, W), device=device, dtype=torch.uint8)
-        st = lib.gd4d_frustum_pe(i2l.data_ptr(), None if m_in is None else m_in.data_ptr(), out.data_ptr(),
-                                 m_out.data_ptr(), B * N, H, W, D, float(pad_h), float(pad_w),
-                                 float(depth_start), float(bin_size), lo_span, _stream_ptr(device))
-        _lib.check(st, "gd4d_frustum_pe")
+        m_ins.append(m_in)
+        xs.append(torch.empty((B * N, 3 * D, H, W), device=device, dtype=torch.float32))
+        ms.append(torch.empty((B, N, H, W), device=device, dtype=torch.uint8))
+    # every level in ONE launch (the coarse levels alone are a few dozen CTAs each); chunks of 8 levels
+    for l0 in range(0, len(xs), 8):
+        n = min(8, len(xs) - l0)
+        ptr = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts[l0:l0 + n]])
+        hs = (C.c_int32 * n)(*[int(h) for h, _ in level_shapes[l0:l0 + n]])
+        ws = (C.c_int32 * n)(*[int(w) for _, w in level_shapes[l0:l0 + n]])
+        st = lib.gd4d_frustum_pe_levels(i2l.data_ptr(), ptr(m_ins), ptr(xs), ptr(ms), B * N, n, hs, ws, D,
+                                        float(pad_h), float(pad_w), float(depth_start), float(bin_size), lo_span,
+                                        _stream_ptr(device))
+        _lib.check(st, "gd4d_frustum_pe_levels")
         _count()
-        xs.append(out)
-        ms.append(m_out.view(torch.bool))
+    ms = [m.view(torch.bool) for m in ms]
     return xs, ms
 
 

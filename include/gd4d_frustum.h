@@ -34,6 +34,15 @@ GD4D_API int gd4d_frustum_pe(const float* img2lidar, const uint8_t* mask_in, flo
                              float pad_h, float pad_w, float depth_start, float bin_size,
                              const float* pc_lo_span, void* cuda_stream);
 
+/* All FPN levels of one forward in ONE launch (the per-level call above is this with num_levels = 1).
+ * mask_in / out / mask_out: HOST arrays of num_levels DEVICE pointers (mask_in, mask_out or single entries may
+ * be NULL); level_h / level_w: HOST arrays.  num_levels <= 8.  position_embeding's per-level loop :427-491. */
+GD4D_API int gd4d_frustum_pe_levels(const float* img2lidar, const uint8_t* const* mask_in, float* const* out,
+                                    uint8_t* const* mask_out, int32_t BN, int32_t num_levels,
+                                    const int32_t* level_h, const int32_t* level_w, int32_t D, float pad_h,
+                                    float pad_w, float depth_start, float bin_size, const float* pc_lo_span,
+                                    void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,7 +64,8 @@ def test_masks_and_sine_embedding_full_geometry(B, T):
     want_masks = fpe_oracle.level_masks(B, N, shapes, metas)
     got_masks = fpe.level_masks(shapes, metas, N)
     for l, (h, w) in enumerate(shapes):
-        assert torch.equal(got_masks[l].cpu(), want_masks[l]) and want_masks[l].any()
+        assert torch.equal(got_masks[l].cpu(), want_masks[l])
+        assert bool(want_masks[l].any()) == (l < 2)             # 900 of 928 rows: only strides 8 and 16 see padding rows
         got = fpe.sine_pe3d((h, w), metas, N, 128, offset=-0.5).cpu().view(B, N, 384, h, w)
         want = fpe_oracle.sine_pe3d(want_masks[l], 128, offset=-0.5)
         assert float((got - want).abs().max()) <= 2e-6          # |sin|,|cos| <= 1: absolute
