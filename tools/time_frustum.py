@@ -18,7 +18,7 @@ s.record()
 for _ in range(30): xs, ms = run()
 e.record(); torch.cuda.synchronize()
 ms_eager = s.elapsed_time(e) / 30                 # includes the host side of 4 ctypes calls + 8 allocations
-# device time: the same 4 launches captured in a CUDA graph (no host work between them); 284 MB written
+# device time: the same launch captured in a CUDA graph (no host work between them); 284 MB written
 # per pass > L2, so back-to-back replays do not hit in cache
 side = torch.cuda.Stream()
 with torch.cuda.stream(side):
@@ -40,4 +40,4 @@ print(json.dumps(dict(kernel="frustum_pe_kernel", cams=6 * T, depth_bins=D, leve
                       algorithmic_bytes=nbytes, achieved_gbs=nbytes / ms_pass / 1e6, peak_gbs=peak,
                       frac=nbytes / ms_pass / 1e6 / peak,
                       us_per_pass_eager=ms_eager * 1e3,
-                      note="4 launches (one per level) replayed from a CUDA graph; eager figure includes the python/ctypes host side; write-only traffic")))
+                      note="ONE launch covering the 4 levels, replayed from a CUDA graph; eager figure includes the python/ctypes host side; write-only traffic")))
