@@ -268,13 +268,16 @@ def measure_decoder(D: Dist, T, dtype, K, W, prewarm_s, keep=False):
     dev = D.dev
     model = build_model(T, dtype, dev, seed=0)              # identical replicas on every rank
     tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
-    # the step's inputs as a producer would hand them over: NCHW maps in the feature dtype, held in ONE
-    # pinned host buffer (bf16 maps travel as bf16: half the PCIe bytes)
+    # The step's inputs as the producer hands them over: NCHW maps held in ONE pinned host buffer in their WIRE
+    # dtype.  f32 workload: the reference's FPN runs under fp16 autocast and returns .float() copies
+    # (detectors/detr3d.py:68), so the synthetic maps are fp16-exact values -- fp32 on the device for BOTH legs,
+    # fp16 on the wire (lossless, half the PCIe bytes; widened by the commit copy).  bf16 workload: bf16 maps.
+    wire = torch.float16 if dtype == "f32" else torch.bfloat16
     shapes = [(1, N, C, h, w) for (h, w) in syn.LEVEL_SHAPES_928x1600]
-    host = HostFeatureBuffer(shapes, tdtype)
+    host = HostFeatureBuffer(shapes, wire)
     for dst, src in zip(host.views, syn.make_feats(1, N, C, syn.LEVEL_SHAPES_928x1600, seed=D.rank)):
-        dst.copy_(src.to(tdtype))
-    feats_dev = [v.to(dev) for v in host.views]
+        dst.copy_(src.to(wire))
+    feats_dev = [v.to(dev).to(tdtype) for v in host.views]
     metas = syn.make_img_metas(1, T)
 
     def forward_loss(feats):
@@ -317,6 +320,24 @@ def measure_decoder(D: Dist, T, dtype, K, W, prewarm_s, keep=False):
         step_e2e()
     st.update(i=0, n=K)                                     # exactly K H2D copies inside the timed region
     ms_e2e = D.timed(step_e2e, K)
+    # the same step with the maps shipped in the compute dtype (fp32 wire for the f32 workload)
+    ms_e2e_wide = wide_bytes = None
+    if wire != tdtype and K > 0:
+        host_w = HostFeatureBuffer(shapes, tdtype)
+        for dst, src in zip(host_w.views, host.views):
+            dst.copy_(src.to(tdtype))
+        stepper.reset_pipeline()
+        narrow, host = host, host_w
+        st.update(primed=False, i=0, n=2)
+        for _ in range(2):
+            step_e2e()
+        st.update(i=0, n=K)
+        ms_e2e_wide = D.timed(step_e2e, K)
+        wide_bytes = host_w.nbytes
+        stepper.reset_pipeline()
+        host = narrow
+        st.update(primed=False)
+        del host_w
     # raw H2D rate of the same buffer on its own (what PCIe / the host gives this rank)
     stepper.prefetch(host)
     torch.cuda.synchronize()
@@ -329,7 +350,11 @@ def measure_decoder(D: Dist, T, dtype, K, W, prewarm_s, keep=False):
     units = D.world * Q * LAYERS                            # query-layer evaluations per step, all ranks
     res = dict(T=T, N=N, dtype=dtype, ms_per_step=ms_res / K, e2e_ms_per_step=ms_e2e / K,
                value=units * K / (ms_res * 1e-3), e2e_value=units * K / (ms_e2e * 1e-3),
-               h2d_bytes=host.nbytes, h2d_GBps_alone=h2d_gbs, launches_per_step=launches_per_step)
+               h2d_bytes=host.nbytes, h2d_GBps_alone=h2d_gbs, launches_per_step=launches_per_step,
+               wire=str(wire).replace("torch.", ""),
+               e2e_wide=None if ms_e2e_wide is None else dict(
+                   value=units * K / (ms_e2e_wide * 1e-3), unit=UNIT, ms_per_step=ms_e2e_wide / K,
+                   h2d_bytes_per_step=wide_bytes, wire=str(tdtype).replace("torch.", "")))
     if keep:
         res["live"] = (model, stepper, metas)
     else:
@@ -375,7 +400,7 @@ def main():
                 workload=workload_name(t2, d2), value=r["value"], unit=UNIT, ms_per_step=r["ms_per_step"],
                 e2e=dict(value=r["e2e_value"], unit=UNIT, ms_per_step=r["e2e_ms_per_step"],
                          h2d_bytes_per_step=r["h2d_bytes"], d2h_bytes_per_step=4,
-                         h2d_GBps_alone=r["h2d_GBps_alone"]),
+                         h2d_GBps_alone=r["h2d_GBps_alone"], wire=r["wire"], same_maps_on_compute_dtype_wire=r["e2e_wide"]),
                 gpu_launches_per_step=r["launches_per_step"])
             if D.rank == 0:
                 m2 = build_model(t2, d2, D.dev, seed=0)
@@ -412,14 +437,21 @@ def main():
                                 optimizer="AdamW (one-launch gd4d_adamw_multi, torch.optim.AdamW arithmetic, device step counter)",
                                 value_proj="fused: gather-then-project (no dense per-pixel GEMM)",
                                 execution="CUDA graphs (fwd+bwd graph; if N>1 one grouped in-place NCCL all-reduce of the batched gradient buffers; optimizer graph)",
-                                features=f"NCHW {dtype} in, packed channel-last once per step inside the step",
+                                features=f"NCHW {dtype} in (fp16-exact values), packed channel-last once per step inside the step",
                                 parallelism=f"dp{D.world}" if D.world > 1 else "single",
                                 l2="inputs larger than L2 (feature maps + dense grad maps >= 2x126 MB per layer)"),
                     e2e=dict(value=head["e2e_value"], unit=UNIT, ms_per_step=head["e2e_ms_per_step"],
                              h2d_bytes_per_step=head["h2d_bytes"], d2h_bytes_per_step=4,
-                             h2d_GBps_alone=head["h2d_GBps_alone"],
+                             h2d_GBps_alone=head["h2d_GBps_alone"], wire=head["wire"],
+                             same_maps_on_compute_dtype_wire=head["e2e_wide"],
                              pipeline="one pinned buffer -> one cudaMemcpyAsync per step on a copy stream, "
-                                      "overlapped with the previous step; one D2D commit; loss D2H + sync"),
+                                      "overlapped with the previous step; one D2D commit (widens the wire dtype); "
+                                      "loss D2H + sync",
+                             wire_note="fp16-exact maps (the reference's FPN runs under fp16 autocast and returns "
+                                       ".float(), detectors/detr3d.py:68) travel as fp16 and are widened on the device: "
+                                       "same values on the device as the resident leg; with 8 ranks copying at once this "
+                                       "box gives GPUs 0-3 22.5 GB/s each (profiles/r2_h2d_probe_n8.json), i.e. 8.4 ms "
+                                       "for 189 MB of fp32 maps"),
                     gpu_launches=head["launches_per_step"] * K, clocks=clocks, roofline=roof,
                     roofline_fwd=roof_fwd, cpu_baseline=cpu_base, extras=extras)
         _emit(line)

@@ -35,7 +35,16 @@ COALESCED_ALLREDUCE = os.environ.get("GD4D_COALESCED_ALLREDUCE", "1") != "0"
 class HostFeatureBuffer:
     """The feature maps of one step in ONE pinned host allocation (``views`` are the per-level
     (B,N,C,H,W) tensors inside it), so that a step's host->device transfer is a single
-    ``cudaMemcpyAsync`` instead of one per level."""
+    ``cudaMemcpyAsync`` instead of one per level.
+
+    ``dtype`` is the WIRE format.  It may be narrower than the dtype the step computes on: the
+    reference's backbone + FPN run under fp16 autocast and hand the head ``.float()`` copies
+    (detectors/detr3d.py:68, ``auto_fp16(apply_to=('img'), out_fp32=True)``; 24 of its 29 configs set
+    ``fp16 = dict(loss_scale=512.)``), so the fp32 maps the decoder consumes are fp16-exact and a
+    ``torch.float16`` host buffer carries them losslessly at half the PCIe bytes; ``commit`` widens them
+    on the device.  (Measured on the 8-GPU box, profiles/r2_h2d_probe_n8.json: with 8 ranks copying at
+    once GPUs 0-3 get 22.5 GB/s each, so 189 MB of fp32 maps cost 8.4 ms per step -- more than the
+    4.9 ms step itself.)"""
 
     def __init__(self, shapes: Sequence[Sequence[int]], dtype: torch.dtype = torch.float32):
         sizes = [int(torch.Size(s).numel()) for s in shapes]
@@ -189,8 +198,12 @@ class GraphedTrainStep:
         ``feats_host``: a ``HostFeatureBuffer`` (ONE copy) or a sequence of pinned tensors (one per level)."""
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=self.device)
+            # the staging buffer has the WIRE dtype of the host buffer (fp16 maps stay fp16 until commit)
+            wire = feats_host.flat.dtype if isinstance(feats_host, HostFeatureBuffer) else None
             if self._static_flat is not None:
-                self._staging_flat, self._staging = _flat_like([f.detach() for f in self.static_feats])
+                like = [f.detach() if wire is None else torch.empty(f.shape, device=self.device, dtype=wire)
+                        for f in self.static_feats]
+                self._staging_flat, self._staging = _flat_like(like)
             else:
                 self._staging_flat, self._staging = None, [torch.empty_like(f) for f in self.static_feats]
             self._staged = torch.cuda.Event()
@@ -208,15 +221,24 @@ class GraphedTrainStep:
                     dst.copy_(src, non_blocking=True)
             self._staged.record(self._copy_stream)
 
+    def reset_pipeline(self):
+        """Forget the staging buffers (the next ``prefetch`` re-creates them for its host buffer's wire dtype)."""
+        if hasattr(self, "_copy_stream"):
+            torch.cuda.synchronize(self.device)
+            for name in ("_copy_stream", "_staging_flat", "_staging", "_staged", "_consumed"):
+                delattr(self, name)
+
     def commit(self, img_metas=None):
-        """Make the prefetched maps the inputs of the next ``step()`` (one D2D copy)."""
+        """Make the prefetched maps the inputs of the next ``step()`` (one D2D copy, which also widens a
+        narrower wire dtype to the compute dtype)."""
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._staged)
         if self._staging_flat is not None:
             if img_metas is not None:
                 modules.lidar2img_device(img_metas, self.device)
             with torch.no_grad():
-                self._static_flat.copy_(self._staging_flat, non_blocking=True)    # one D2D for all levels
+                # one D2D for all levels; widens fp16 / bf16 wire maps to the compute dtype on the way
+                self._static_flat.copy_(self._staging_flat, non_blocking=True)
         else:
             self.set_inputs(self._staging, img_metas)
         self._consumed.record(cur)
