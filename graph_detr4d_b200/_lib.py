@@ -13,7 +13,7 @@ import threading
 
 from . import _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LEVELS = 8
 MODE_A, MODE_C, MODE_V2 = 0, 1, 2
 F32, BF16 = 0, 1
@@ -27,6 +27,7 @@ EXPORTS = (
     "gd4d_xview_launch_info",
     "gd4d_xview_forward",
     "gd4d_xview_backward",
+    "gd4d_xview_bwd_ws_bytes",
     "gd4d_pack_nchw",
     "gd4d_unpack_nhwc",
     # include/gd4d_glue.h
@@ -86,6 +87,8 @@ class XViewParams(C.Structure):
         ("grad_offsets", C.c_void_p),
         ("grad_cam_logits", C.c_void_p),
         ("grad_ref", C.c_void_p),
+        ("bwd_ws", C.c_void_p),
+        ("bwd_ws_bytes", C.c_int64),
     ]
 
 
@@ -128,6 +131,8 @@ def load(build_if_missing: bool = True):
         lib.gd4d_xview_forward.argtypes = [C.POINTER(XViewParams), C.c_void_p]
         lib.gd4d_xview_backward.restype = C.c_int
         lib.gd4d_xview_backward.argtypes = [C.POINTER(XViewParams), C.c_void_p]
+        lib.gd4d_xview_bwd_ws_bytes.restype = C.c_int64
+        lib.gd4d_xview_bwd_ws_bytes.argtypes = [C.POINTER(XViewParams)]
         lib.gd4d_pack_nchw.restype = C.c_int
         lib.gd4d_pack_nchw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p]

@@ -5,6 +5,8 @@
 namespace gd4d {
 int dispatch_forward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
 int dispatch_backward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
+int dispatch_backward_sorted(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
+long long sorted_ws_bytes(const gd4d_xview_params& p);
 int dispatch_forward_tma(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
 int dispatch_v2(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream, bool backward);
 int dispatch_pack(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t images, int C,
@@ -129,7 +131,19 @@ int gd4d_xview_backward(const gd4d_xview_params* p, void* cuda_stream) {
   if (st != GD4D_OK) return st;
   if (p->mode == GD4D_MODE_V2)
     return gd4d::dispatch_v2(*p, g, static_cast<cudaStream_t>(cuda_stream), true);
+  if (p->mode == GD4D_MODE_C && p->wide && p->bwd_ws != nullptr)
+    return gd4d::dispatch_backward_sorted(*p, g, static_cast<cudaStream_t>(cuda_stream));
   return gd4d::dispatch_backward(*p, g, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int64_t gd4d_xview_bwd_ws_bytes(const gd4d_xview_params* p) {
+  gd4d::LaunchGeom g{};
+  const int st = gd4d::validate(p, false, &g);
+  if (st != GD4D_OK && st != GD4D_ERR_NULL) return st;      // `out` may be unset: only the dimensions matter
+  if (p == nullptr) return GD4D_ERR_NULL;
+  if (p->mode != GD4D_MODE_C || !p->wide) return GD4D_ERR_UNSUPPORTED;
+  const long long n = gd4d::sorted_ws_bytes(*p);
+  return n < 0 ? GD4D_ERR_DIMS : n;
 }
 
 int gd4d_pack_nchw(const void* src, void* dst, int32_t src_dtype, int32_t dst_dtype, int64_t images,

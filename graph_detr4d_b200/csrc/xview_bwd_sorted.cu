@@ -1,0 +1,457 @@
+// Sorted ("owner computes") backward of the wide cross-view sampling kernel (mode C, wide = 1).
+//
+// Why: the atomics backward (xview_bwd.cu) issues one 1 KB vector reduction PER CORNER READ into the
+// shared fp32 grad map -- 486 k reductions = 497 MB through the L2 atomic units per launch at N = 6,
+// 54 of them on the same row at the coarsest level.  ncu (profiles/r2_xview_kernels_ncu_full.csv) and
+// the L2 roofs (profiles/l2_peaks.json: red.add.v4.f32 4.6-5.6 TB/s) put that kernel at 0.83 of the
+// L2-atomic roof and 0.36 of HBM.  But only 96 k DISTINCT rows are touched (5x reuse; 2x at level 0,
+// 54x at level 3).  So: sort the corner contributions by pixel row and let one warp own a run of equal
+// rows -- it loads the value row ONCE, gathers grad_out rows (7 MB, L2-resident) for the run's
+// contributions, forms the dot products the small gradients need AND the row's feature gradient in
+// registers, and retires the row with ONE reduction.  Reductions drop 486 k -> ~110 k, value-row
+// gathers 486 k -> ~110 k.
+//
+// Five stream-ordered launches (all through gd4d_xview_backward when p.bwd_ws is set):
+//   K1 emit      warp per (b,q,head): candidates + records exactly as xview_bwd.cu builds them; every
+//                in-map corner takes a slot in its row's histogram (atomicAdd returns its rank) and
+//                writes {row, rank, grad_out row, wt * w_corner} at cid = base + item*4 + corner
+//   K2 scan      exclusive prefix over the row histogram (block-local + last-block-done carry scan)
+//   K3 scatter   contribution -> its sorted position row_start[row] + rank
+//   K4 owner     warp per 32 consecutive sorted contributions (perfectly balanced; a row that spans
+//                warps is simply reduced by each): value row loaded at run starts only, 4 grad_out
+//                rows in flight, dot -> dots[cid], acc += coef * g, red.add.v4.f32 at run ends;
+//                also re-zeroes the histogram entries it consumed
+//   K5 finish    warp per (b,q,head), ONE LANE PER ITEM: rebuilds the same records, reads its 4 dots
+//                and does what the tail of xview_bwd.cu does (softmax / sigmoid / projection chain)
+// Results equal xview_bwd.cu up to fp32 summation order (tests/test_xview_gpu.py runs both).
+#include "xview_common.cuh"
+#include "xview_bwd_records.cuh"
+
+namespace gd4d {
+
+struct SortedWs {
+  unsigned* counters;   // [0] slots handed out by K1 (4 per item), [1] number of sorted contributions,
+                        // [2] K2 blocks done
+  int* row_count;       // R    histogram; zero on entry, re-zeroed by K4
+  int* row_start;       // R    block-local exclusive prefix
+  int* block_sums;      // nblk exclusive prefix of the 2048-row block totals
+  int* base;            // B*Q*Hh  first cid of each (b,q,head)
+  int4* rec;            // cap  {row | -1, rank, grad_out row, coef bits}
+  int4* sorted;         // cap  {row, grad_out row, coef bits, cid}
+  float* dots;          // cap  value_row . grad_out_row per contribution
+  long long level_row0[GD4D_MAX_LEVELS + 1];   // first global row of each level (+ total)
+  int R, nblk;
+  long long cap;
+};
+
+constexpr int kScanBlock = 2048;   // rows per K2 block (256 threads x 8)
+
+static long long ws_layout(const gd4d_xview_params& p, SortedWs* ws, char* base_ptr) {
+  long long R = 0;
+  for (int l = 0; l < p.L; ++l) {
+    if (ws) ws->level_row0[l] = R;
+    R += static_cast<long long>(p.B) * p.N * p.level_h[l] * p.level_w[l];
+  }
+  if (R > 0x7ffffff0LL) return -1;
+  const long long items = static_cast<long long>(p.B) * p.Q * p.Hh * p.N * p.P * p.L;
+  const long long cap = items * 4;
+  if (cap > 0x7ffffff0LL) return -1;
+  const long long nblk = (R + kScanBlock - 1) / kScanBlock;
+  long long off = 0;
+  auto take = [&](long long bytes) { const long long o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const long long o_cnt = take(16), o_rc = take(R * 4), o_rs = take(R * 4), o_bs = take(nblk * 4);
+  const long long o_base = take(static_cast<long long>(p.B) * p.Q * p.Hh * 4);
+  const long long o_rec = take(cap * 16), o_sorted = take(cap * 16), o_dots = take(cap * 4);
+  if (ws) {
+    ws->level_row0[p.L] = R;
+    ws->R = static_cast<int>(R); ws->nblk = static_cast<int>(nblk); ws->cap = cap;
+    ws->counters = reinterpret_cast<unsigned*>(base_ptr + o_cnt);
+    ws->row_count = reinterpret_cast<int*>(base_ptr + o_rc);
+    ws->row_start = reinterpret_cast<int*>(base_ptr + o_rs);
+    ws->block_sums = reinterpret_cast<int*>(base_ptr + o_bs);
+    ws->base = reinterpret_cast<int*>(base_ptr + o_base);
+    ws->rec = reinterpret_cast<int4*>(base_ptr + o_rec);
+    ws->sorted = reinterpret_cast<int4*>(base_ptr + o_sorted);
+    ws->dots = reinterpret_cast<float*>(base_ptr + o_dots);
+  }
+  return off;
+}
+
+long long sorted_ws_bytes(const gd4d_xview_params& p) { return ws_layout(p, nullptr, nullptr); }
+
+// ------------------------------------------------------------------------------------------------
+// K1 emit / K5 finish: one kernel body, warp per (b, q, head), one LANE per (candidate, level) item
+// ------------------------------------------------------------------------------------------------
+template <typename VT, bool FINISH>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+xview_bwd_items_kernel(const __grid_constant__ gd4d_xview_params p, const __grid_constant__ SortedWs ws,
+                       const int cand_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const size_t warp_bytes = sizeof(float) * kMaxLP * 5 + sizeof(CandB) * cand_cap;
+  float* sw = reinterpret_cast<float*>(smem_raw + warp * warp_bytes);   // softmax weights
+  float* gsum = sw + kMaxLP;                                              // sum_n wcam*(s.g) per (l,p)
+  float* doff = gsum + kMaxLP;                                            // dL/d offset (p,3)
+  CandB* cands = reinterpret_cast<CandB*>(doff + 3 * kMaxLP);
+  const int LP = p.L * p.P;
+  if (FINISH && blockIdx.x == 0 && threadIdx.x == 0) {   // K3 / K4 are done with them: ready for the next call
+    ws.counters[0] = 0u; ws.counters[1] = 0u; ws.counters[2] = 0u;
+  }
+
+  WorkIter wi;
+  work_begin(p, wi);
+  WarpCtx w;
+  while (work_next(p, wi, w)) {
+    head_softmax(p, w, sw);
+    if (FINISH) {
+      gsum[lane] = 0.f;
+      gsum[lane + 32] = 0.f;
+      for (int i = lane; i < 3 * kMaxLP; i += 32) doff[i] = 0.f;
+    }
+    const int nvalid = build_candidates<GD4D_MODE_C, CandB>(p, w, cands, false);
+    const int total = nvalid * p.L;
+    const int gw = w.bq * p.Hh + w.h;
+    int base;
+    if (FINISH) {
+      base = ws.base[gw];
+    } else {
+      unsigned v = 0;
+      if (lane == 0 && total > 0) v = atomicAdd(ws.counters, static_cast<unsigned>(4 * total));
+      base = static_cast<int>(__shfl_sync(0xffffffffu, v, 0));
+      if (lane == 0) ws.base[gw] = base;
+    }
+    const int go_row = (w.b * p.Hh + w.h) * p.Q + w.q;
+    const float gws = (FINISH && p.grad_wsum != nullptr) ? __ldg(p.grad_wsum + go_row) : 0.f;
+
+    for (int item = lane; item < total; item += 32) {
+      const RecB r = build_record_bwd<GD4D_MODE_C, VT, true>(p, cands, sw, item, total, w);
+      const int l = r.meta & 0xff;
+      const long long z = (reinterpret_cast<const char*>(g_zero_row) - static_cast<const char*>(p.value[l])) /
+                          static_cast<long long>(sizeof(VT));
+      const long long o[4] = {r.o00, r.o01, r.o10, r.o11};
+      const int cid0 = base + item * 4;
+      if (!FINISH) {
+        const float cw[4] = {r.wt * r.w00, r.wt * r.w01, r.wt * r.w10, r.wt * r.w11};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int4 rec = make_int4(-1, 0, 0, 0);
+          if (o[j] != z) {                                       // in-map corner
+            const int row = static_cast<int>(ws.level_row0[l] + o[j] / p.C);
+            rec = make_int4(row, atomicAdd(ws.row_count + row, 1), go_row, __float_as_int(cw[j]));
+          }
+          ws.rec[cid0 + j] = rec;
+        }
+      } else {
+        float d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = (o[j] != z) ? ws.dots[cid0 + j] : 0.f;
+        float sdot = r.w00 * d[0] + r.w01 * d[1] + r.w10 * d[2] + r.w11 * d[3];
+        float dxdot = r.ax00 * d[0] + r.ax01 * d[1] + r.ax10 * d[2] + r.ax11 * d[3];   // W * ds/dix . g
+        float dydot = r.ay00 * d[0] + r.ay01 * d[1] + r.ay10 * d[2] + r.ay11 * d[3];   // H * ds/diy . g
+        // the bias rides as an all-ones channel: 1 inside the map, 0 outside
+        sdot += gws * (r.w00 + r.w01 + r.w10 + r.w11);
+        dxdot += gws * (r.ax00 + r.ax01 + r.ax10 + r.ax11);
+        dydot += gws * (r.ay00 + r.ay01 + r.ay10 + r.ay11);
+        const int k = (r.meta >> 16) & 0x7fff;
+        atomicAdd(&cands[k].du, r.wt * dxdot);
+        atomicAdd(&cands[k].dv, r.wt * dydot);
+        atomicAdd(&gsum[(r.meta >> 8) & 0xff], r.cw * sdot);
+        atomicAdd(&cands[k].cg, r.smw * sdot);
+      }
+    }
+    __syncwarp();
+    if (FINISH) {
+      if (p.grad_attn_logits != nullptr) {   // softmax backward: dlogit_j = sm_j * (G_j - sum_k sm_k G_k)
+        const float s0 = sw[lane], s1 = sw[lane + 32];
+        const float g0 = gsum[lane], g1 = gsum[lane + 32];
+        float dot = s0 * g0 + s1 * g1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        float* ga = p.grad_attn_logits + attn_row_off(p, w);
+        if (lane < LP) atomicAdd(ga + lane, s0 * (g0 - dot));
+        if (lane + 32 < LP) atomicAdd(ga + lane + 32, s1 * (g1 - dot));
+      }
+      float rX = 0.f, rY = 0.f, rZ = 0.f;
+      for (int k = lane; k < nvalid; k += 32) {
+        const CandB cd = cands[k];
+        const int n = cd.np >> 8;
+        const int pi = cd.np & 0xff;
+        const float* M = p.lidar2img + (static_cast<size_t>(w.b) * p.N + n) * 16;
+        const float dcx = cd.du / (cd.den * p.img_w);
+        const float dcy = cd.dv / (cd.den * p.img_h);
+        const float dcz = -(cd.du * cd.u + cd.dv * cd.v) / cd.den;  // valid => cz > eps => d den/d cz = 1
+        const float dX = __ldg(M + 0) * dcx + __ldg(M + 4) * dcy + __ldg(M + 8) * dcz;
+        const float dY = __ldg(M + 1) * dcx + __ldg(M + 5) * dcy + __ldg(M + 9) * dcz;
+        const float dZ = __ldg(M + 2) * dcx + __ldg(M + 6) * dcy + __ldg(M + 10) * dcz;
+        rX += dX; rY += dY; rZ += dZ;
+        atomicAdd(&doff[pi * 3 + 0], dX);
+        atomicAdd(&doff[pi * 3 + 1], dY);
+        atomicAdd(&doff[pi * 3 + 2], dZ);
+        if (p.grad_cam_logits != nullptr)
+          atomicAdd(p.grad_cam_logits + cam_off(p, w, n), cd.w * (1.f - cd.w) * cd.cg);
+      }
+      if (p.grad_ref != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          rX += __shfl_xor_sync(0xffffffffu, rX, o);
+          rY += __shfl_xor_sync(0xffffffffu, rY, o);
+          rZ += __shfl_xor_sync(0xffffffffu, rZ, o);
+        }
+        if (lane == 0 && nvalid > 0) {
+          float* gr = p.grad_ref + static_cast<size_t>(w.bq) * 3;
+          atomicAdd(gr + 0, rX * p.pc_span[0]);
+          atomicAdd(gr + 1, rY * p.pc_span[1]);
+          atomicAdd(gr + 2, rZ * p.pc_span[2]);
+        }
+      }
+      if (p.grad_offsets != nullptr) {
+        __syncwarp();
+        float* go = p.grad_offsets + offsets_row_off(p, w);
+        for (int i = lane; i < p.P * 3; i += 32) atomicAdd(go + i, doff[i]);
+      }
+    }
+    __syncwarp();  // per-warp shared-memory state is reused by the next work item
+  }
+  work_end(p, wi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: exclusive prefix of the row histogram
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xview_bwd_scan_kernel(const SortedWs ws) {
+  __shared__ int warp_tot[8];
+  __shared__ int carry_s;
+  __shared__ bool last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = blockIdx.x * kScanBlock + tid * 8;
+  int v[8], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = (r0 + i < ws.R) ? ws.row_count[r0 + i] : 0;
+    sum += v[i];
+  }
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  int wbase = 0;
+  for (int i = 0; i < warp; ++i) wbase += warp_tot[i];
+  int run = wbase + inc - sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (r0 + i < ws.R) ws.row_start[r0 + i] = run;
+    run += v[i];
+  }
+  if (tid == 255) {
+    ws.block_sums[blockIdx.x] = run;             // block total
+    __threadfence();
+    last = atomicAdd(ws.counters + 2, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  // the last block to finish turns the block totals into exclusive prefixes (256 at a time)
+  __threadfence();
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < ws.nblk; b0 += 256) {
+    const int i = b0 + tid;
+    const int x = i < ws.nblk ? *(volatile int*)(ws.block_sums + i) : 0;
+    int s = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane == 31) warp_tot[warp] = s;
+    __syncthreads();
+    int wb = carry_s;
+    for (int k = 0; k < warp; ++k) wb += warp_tot[k];
+    if (i < ws.nblk) ws.block_sums[i] = wb + s - x;
+    __syncthreads();
+    if (tid == 255) carry_s = wb + s;
+    __syncthreads();
+  }
+  if (tid == 0) ws.counters[1] = static_cast<unsigned>(carry_s);   // number of sorted contributions
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: scatter every contribution to its sorted position
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xview_bwd_scatter_kernel(const SortedWs ws) {
+  const unsigned n = ws.counters[0];
+  for (unsigned cid = blockIdx.x * blockDim.x + threadIdx.x; cid < n; cid += gridDim.x * blockDim.x) {
+    const int4 r = ws.rec[cid];
+    if (r.x < 0) continue;
+    const int pos = ws.row_start[r.x] + ws.block_sums[r.x / kScanBlock] + r.y;
+    ws.sorted[pos] = make_int4(r.x, r.z, r.w, static_cast<int>(cid));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: owner pass
+// ------------------------------------------------------------------------------------------------
+// retire one run: the row's feature gradient leaves with ONE vector reduction per lane vector
+template <typename VT, int NV>
+__device__ __forceinline__ void flush_row(const gd4d_xview_params& p, const SortedWs& ws, int row,
+                                          const float (&acc)[Slice<VT>::VEC * NV], int lane) {
+  constexpr int VEC = Slice<VT>::VEC;
+  constexpr int GV = VEC / 4;
+  if (row < 0) return;
+  int l = 0;
+  while (l + 1 < p.L && row >= ws.level_row0[l + 1]) ++l;
+  if (lane == 0) ws.row_count[row] = 0;                            // histogram ready for the next call
+  float* gv = p.grad_value[l];
+  if (gv == nullptr) return;
+  gv += (static_cast<long long>(row) - ws.level_row0[l]) * p.C;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int k = 0; k < GV; ++k) {
+      const int ch = (j * 32 + lane) * VEC + k * 4;
+      red_add_v4(gv + ch, acc[j * VEC + k * 4], acc[j * VEC + k * 4 + 1], acc[j * VEC + k * 4 + 2],
+                 acc[j * VEC + k * 4 + 3]);
+    }
+}
+
+template <typename VT, int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+xview_bwd_owner_kernel(const __grid_constant__ gd4d_xview_params p, const __grid_constant__ SortedWs ws) {
+  constexpr int VEC = Slice<VT>::VEC;     // channels per 16-byte value load
+  constexpr int PL = VEC * NV;            // channels per lane
+  constexpr int GV = VEC / 4;             // float4 per value vector in the fp32 grad_out / grad map rows
+  constexpr int U = PL > 8 ? 2 : 4;       // contributions in flight (16-channel lanes: 2, or the batch spills)
+  const int lane = threadIdx.x & 31;
+  const int n = static_cast<int>(ws.counters[1]);
+  const int nchunks = (n + 31) / 32;
+  const int warps = gridDim.x * kWarpsPerCta;
+
+  for (int c = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); c < nchunks; c += warps) {
+    float acc[PL];
+#pragma unroll
+    for (int i = 0; i < PL; ++i) acc[i] = 0.f;
+    float vprev[PL];
+#pragma unroll
+    for (int i = 0; i < PL; ++i) vprev[i] = 0.f;
+    int prev_row = -1;
+
+    const int i0 = c * 32;
+    const int cnt = min(32, n - i0);
+    for (int u0 = 0; u0 < cnt; u0 += U) {
+      int4 rc[U];
+      bool ok[U], start[U];
+      uint4 vraw[U][NV];
+      float4 graw[U][NV][GV];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ok[u] = u0 + u < cnt;
+        rc[u] = ok[u] ? __ldg(ws.sorted + i0 + u0 + u) : make_int4(-1, 0, 0, 0);   // warp-uniform load
+        const int before = (u == 0) ? prev_row : rc[u - 1].x;
+        start[u] = ok[u] && rc[u].x != before;
+        int l = 0;
+        while (l + 1 < p.L && rc[u].x >= ws.level_row0[l + 1]) ++l;
+        const VT* vrow = static_cast<const VT*>(p.value[l]) +
+                         (static_cast<long long>(max(rc[u].x, 0)) - ws.level_row0[l]) * p.C;
+        const float* grow = p.grad_out + static_cast<long long>(rc[u].y) * p.C;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int ch = (j * 32 + lane) * VEC;
+          vraw[u][j] = ldg_nc_v4(vrow + ch, start[u]);             // run starts only
+#pragma unroll
+          for (int k = 0; k < GV; ++k) {
+            const uint4 t = ldg_nc_v4(grow + ch + k * 4, ok[u]);
+            graw[u][j][k] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z),
+                                        __uint_as_float(t.w));
+          }
+        }
+      }
+      float dot[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (start[u]) {                                            // warp-uniform
+          flush_row<VT, NV>(p, ws, prev_row, acc, lane);
+#pragma unroll
+          for (int i = 0; i < PL; ++i) acc[i] = 0.f;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) Slice<VT>::unpack(vraw[u][j], vprev + j * VEC);
+          prev_row = rc[u].x;
+        }
+        const float coef = __int_as_float(rc[u].z);
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+          for (int k = 0; k < GV; ++k) {
+            const float4 g = graw[u][j][k];
+            const int b = j * VEC + k * 4;
+            d = fmaf(vprev[b], g.x, d);     d = fmaf(vprev[b + 1], g.y, d);
+            d = fmaf(vprev[b + 2], g.z, d); d = fmaf(vprev[b + 3], g.w, d);
+            acc[b] = fmaf(coef, g.x, acc[b]);         acc[b + 1] = fmaf(coef, g.y, acc[b + 1]);
+            acc[b + 2] = fmaf(coef, g.z, acc[b + 2]); acc[b + 3] = fmaf(coef, g.w, acc[b + 3]);
+          }
+        dot[u] = d;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u] && lane == u) ws.dots[rc[u].w] = dot[u];
+    }
+    flush_row<VT, NV>(p, ws, prev_row, acc, lane);
+  }
+}
+
+template <typename VT>
+static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const SortedWs& ws, cudaStream_t stream) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return GD4D_ERR_CUDA;
+  const int block = kWarpsPerCta * 32;
+  const int smem = static_cast<int>((sizeof(float) * kMaxLP * 5 + sizeof(CandB) * g.cand_cap) * kWarpsPerCta);
+  auto emit = xview_bwd_items_kernel<VT, false>;
+  auto finish = xview_bwd_items_kernel<VT, true>;
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(emit, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(finish, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return GD4D_ERR_CUDA;
+  }
+  auto items_grid = [&](auto kern) -> int {
+    int grid = g.grid;
+    if (p.sched != nullptr) {   // persistent grid: one resident wave, warps claim work dynamically
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem) != cudaSuccess) return -1;
+      const long long resident = static_cast<long long>(sms) * (occ > 0 ? occ : 1);
+      if (resident < grid) grid = static_cast<int>(resident);
+    }
+    return grid;
+  };
+  const int g1 = items_grid(emit), g5 = items_grid(finish);
+  if (g1 <= 0 || g5 <= 0) return GD4D_ERR_CUDA;
+  emit<<<g1, block, smem, stream>>>(p, ws, g.cand_cap);
+  xview_bwd_scan_kernel<<<ws.nblk, 256, 0, stream>>>(ws);
+  xview_bwd_scatter_kernel<<<sms * 4, 256, 0, stream>>>(ws);
+  if (g.nv == 1) xview_bwd_owner_kernel<VT, 1><<<sms * 2, block, 0, stream>>>(p, ws);
+  else xview_bwd_owner_kernel<VT, 2><<<sms * 2, block, 0, stream>>>(p, ws);
+  finish<<<g5, block, smem, stream>>>(p, ws, g.cand_cap);
+  return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
+}
+
+int dispatch_backward_sorted(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream) {
+  if (p.mode != GD4D_MODE_C || !p.wide || p.bwd_ws == nullptr) return GD4D_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(p.bwd_ws) & 255u) != 0) return GD4D_ERR_ALIGN;
+  SortedWs ws;
+  const long long need = ws_layout(p, &ws, static_cast<char*>(p.bwd_ws));
+  if (need < 0) return GD4D_ERR_DIMS;
+  if (p.bwd_ws_bytes < need) return GD4D_ERR_DIMS;
+  return p.value_dtype == GD4D_BF16 ? launch_sorted<__nv_bfloat16>(p, g, ws, stream)
+                                    : launch_sorted<float>(p, g, ws, stream);
+}
+
+}  // namespace gd4d

@@ -24,6 +24,12 @@ __all__ = ["XViewConfig", "GenLayout", "pack_features", "PackedFeatures", "xview
 DYNAMIC_SCHEDULE = True   # persistent grid + work counter (False: one warp per item, static)
 TMA_FORWARD = False       # wide forward through the cp.async.bulk staging path (xview_fwd_tma.cu)
 L2_PREFETCH = os.environ.get("GD4D_L2_PREFETCH", "0") != "0"   # prefetch.global.L2 of the next batch's rows
+# wide backward, opt-in (GD4D_SORTED_BWD=1): sort the corner contributions by pixel row, one warp owns a run
+# (xview_bwd_sorted.cu, 5 launches) instead of one vector reduction per corner read (xview_bwd.cu, 1 launch).
+# Measured r2 (profiles/r2_bwd_variants.json): it cuts the DRAM+L2-atomic traffic as designed (owner kernel
+# 274 MB DRAM, 110 k reductions instead of 486 k) but its first version is instruction-bound (132 warp
+# instructions per contribution) and 199 us vs 141 us end to end at N = 6 -- so the atomics kernel stays default.
+SORTED_BACKWARD = os.environ.get("GD4D_SORTED_BWD", "0") != "0"
 _LAUNCHES = 0      # kernels of libgd4d_xview.so launched by this process (bench: gpu_launches)
 
 
@@ -62,6 +68,33 @@ def _sched_ptr(device) -> int:
             t = torch.zeros(2, dtype=torch.int32, device=device)
         _SCHED[key] = t
     return t.data_ptr()
+
+
+_BWD_WS = {}
+
+
+def _attach_bwd_ws(p: XViewParams, device) -> int:
+    """Scratch of the sorted wide backward, one per (device, stream) like the work counter: its
+    counters + row histogram are zeroed once here, every launch leaves them zeroed again.
+    Returns the number of kernels the backward call will launch."""
+    if not (SORTED_BACKWARD and p.wide and p.mode == MODE_C):
+        return 1
+    need = int(_lib.load().gd4d_xview_bwd_ws_bytes(C.byref(p)))
+    if need < 0:
+        _lib.check(need, "gd4d_xview_bwd_ws_bytes")
+    key = (torch.device(device).index, _stream_ptr(device))
+    t = _BWD_WS.get(key)
+    rows = sum(p.B * p.N * p.level_h[l] * p.level_w[l] for l in range(p.L))
+    head = 256 + (4 * rows + 255) // 256 * 256
+    if t is None or t.numel() < need or t._gd4d_rows != rows:
+        with torch.no_grad():
+            t = torch.empty(need, dtype=torch.uint8, device=device)
+            t[:head].zero_()
+        t._gd4d_rows = rows          # a different row count moves the regions: start from a clean histogram
+        _BWD_WS[key] = t
+    p.bwd_ws = t.data_ptr()
+    p.bwd_ws_bytes = t.numel()
+    return 5
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -399,9 +432,10 @@ def xview_backward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: 
     p.grad_offsets = g_off.data_ptr() if g_off is not None else None
     p.grad_cam_logits = g_cam.data_ptr() if g_cam is not None else None
     p.grad_ref = g_ref.data_ptr() if g_ref is not None else None
+    n_launch = _attach_bwd_ws(p, ref.device)
     st = _lib.load().gd4d_xview_backward(C.byref(p), _stream_ptr(ref.device))
     _lib.check(st, "gd4d_xview_backward")
-    _count()
+    _count(n_launch)
     return g_attn, g_off, g_cam, g_ref
 
 
@@ -409,14 +443,15 @@ class PreparedLaunch:
     """A fully-filled parameter block that can be re-launched without any host-side
     tensor bookkeeping (kernel-only timing loops, CUDA-graph capture)."""
 
-    def __init__(self, fn, what, params, device, keepalive):
+    def __init__(self, fn, what, params, device, keepalive, kernels=1):
         self._fn, self._what, self.params, self._device, self._keep = fn, what, params, device, keepalive
+        self.kernels = kernels
 
     def launch(self):
         st = self._fn(C.byref(self.params), _stream_ptr(self._device))
         if st != 0:
             _lib.check(st, self._what)
-        _count()
+        _count(self.kernels)
 
 
 def prepare_forward(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, lidar2img) -> PreparedLaunch:
@@ -458,9 +493,10 @@ def prepare_backward(cfg, values, B, N, ref, attn_logits, offsets, cam_logits, l
     if cam_logits is not None:
         smalls.append(torch.zeros_like(cam_logits))
         p.grad_cam_logits = smalls[-1].data_ptr()
+    n_launch = _attach_bwd_ws(p, ref.device)
     return PreparedLaunch(_lib.load().gd4d_xview_backward, "gd4d_xview_backward", p, ref.device,
                           (list(values), ref, attn_logits, offsets, cam_logits, lidar2img, grad_out,
-                           grad_wsum, list(grad_values), smalls))
+                           grad_wsum, list(grad_values), smalls), kernels=n_launch)
 
 
 def _check_gen(cfg, B, N, L, ref, gen, layout: GenLayout, lidar2img):
@@ -526,8 +562,9 @@ def xview_backward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layou
     p.grad_offsets = base + 4 * layout.offsets
     p.grad_cam_logits = base + 4 * layout.cam
     p.grad_ref = g_ref.data_ptr() if g_ref is not None else None
+    n_launch = _attach_bwd_ws(p, ref.device)
     _lib.check(_lib.load().gd4d_xview_backward(C.byref(p), _stream_ptr(ref.device)), "gd4d_xview_backward")
-    _count()
+    _count(n_launch)
     return g_gen, g_ref
 
 

@@ -40,7 +40,7 @@ extern "C" {
 #define GD4D_API
 #endif
 
-#define GD4D_ABI_VERSION 5
+#define GD4D_ABI_VERSION 6
 #define GD4D_MAX_LEVELS 8
 
 typedef enum gd4d_status {
@@ -153,6 +153,14 @@ typedef struct gd4d_xview_params {
   float* grad_offsets;
   float* grad_cam_logits;
   float* grad_ref;
+  /* backward, mode C wide only: scratch of at least gd4d_xview_bwd_ws_bytes() bytes, 256-byte aligned,
+   * ZERO on first use (the launch leaves its counters and histogram zeroed again, so the same scratch
+   * serves every later backward ON THE SAME STREAM without a memset).  When set, the backward sorts the
+   * corner contributions by pixel row and lets one warp own each run (csrc/xview_bwd_sorted.cu): one
+   * reduction per distinct row per 32 contributions instead of one per corner read.  NULL: the
+   * atomics-per-corner kernel (csrc/xview_bwd.cu).  Same results up to fp32 summation order. */
+  void* bwd_ws;
+  int64_t bwd_ws_bytes;
 } gd4d_xview_params;
 
 GD4D_API int gd4d_abi_version(void);
@@ -167,6 +175,8 @@ GD4D_API int gd4d_xview_launch_info(const gd4d_xview_params* p, int32_t* grid, i
 
 GD4D_API int gd4d_xview_forward(const gd4d_xview_params* p, void* cuda_stream);
 GD4D_API int gd4d_xview_backward(const gd4d_xview_params* p, void* cuda_stream);
+/* bytes of bwd_ws the sorted backward needs for these dimensions (mode C, wide); negative status otherwise */
+GD4D_API int64_t gd4d_xview_bwd_ws_bytes(const gd4d_xview_params* p);
 
 /* NCHW (images, C, H, W) -> channel-last (images, H, W, C) with optional cast.
  * src_dtype/dst_dtype: gd4d_dtype (fp32->fp32, fp32->bf16, bf16->bf16). */

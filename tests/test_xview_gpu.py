@@ -216,6 +216,45 @@ def test_mode_c_wide_forward_backward(C, dtype, T, Q):
         assert H.rel_err(fg.grad.cpu(), fo.grad) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("dtype,T,B,static", [(torch.float32, 1, 1, False), (torch.float32, 2, 2, False),
+                                              (torch.bfloat16, 2, 1, False), (torch.float32, 1, 1, True)])
+def test_sorted_backward_equals_atomics_backward_and_leaves_its_scratch_clean(dtype, T, B, static):
+    """The owner-computes backward (xview_bwd_sorted.cu: sort by pixel row, one reduction per run) against
+    the atomics backward (xview_bwd.cu): same gradients up to fp32 summation order; calling it three
+    times on one scratch gives the same answer (its counters and histogram are left zeroed); with the
+    static one-warp-per-item schedule too; NULL feature-gradient maps are skipped."""
+    sc = H.scene(B=B, T=T, Q=333)
+    logits, offsets, cam = H.rand_inputs_c(sc)
+    packed = _pack(sc["feats"], dtype)
+    cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=True)
+    args = (cfg, packed.levels, B, sc["N"], sc["ref"].cuda(), logits.cuda(), offsets.cuda(), cam.cuda(),
+            sc["l2i"].cuda())
+    g = torch.Generator().manual_seed(3)
+    go = torch.randn(B, 8, 333, 256, generator=g).cuda()
+    gw = torch.randn(B, 8, 333, generator=g).cuda()
+    res = {}
+    ops.DYNAMIC_SCHEDULE = not static
+    try:
+        for srt in (False, True, True, True):
+            ops.SORTED_BACKWARD = srt
+            gv = [torch.zeros(v.shape, device="cuda") for v in packed.levels]
+            n0 = ops.launch_count()
+            small = ops.xview_backward(*args, go, gv, grad_wsum=gw)
+            assert ops.launch_count() - n0 == (5 if srt else 1)
+            res.setdefault(srt, []).append((gv, small))
+        small_only = ops.xview_backward(*args, go, None, grad_wsum=gw)      # no feature gradients wanted
+    finally:
+        ops.SORTED_BACKWARD, ops.DYNAMIC_SCHEDULE = False, True
+    gv_a, small_a = res[False][0]
+    for gv_s, small_s in res[True]:
+        for a, b in zip(gv_s, gv_a):
+            assert H.rel_err(a, b) <= 1e-5 and float(b.abs().max()) > 0
+        for a, b in zip(small_s, small_a):
+            assert H.rel_err(a, b) <= 2e-5
+    for a, b in zip(small_only, small_a):
+        assert H.rel_err(a, b) <= 2e-5
+
+
 def test_grad_sink_is_shared_across_layers():
     """Six 'layers' sampling the same packed maps must accumulate into ONE grad map."""
     sc = H.scene(B=1, T=1, Q=40)
