@@ -90,6 +90,31 @@ GD4D_API int gd4d_adamw_multi(const gd4d_adamw_tensor* table_dev, const int32_t*
                               int32_t n_blocks, const float* step_dev, float lr, float beta1,
                               float beta2, float eps, float weight_decay, void* cuda_stream);
 
+/* fp32-accurate GEMM on the tensor cores (csrc/gemm_tf32x3.cu): C[M,N] = A . B^T (+ bias[N]) (relu), error-
+ * compensated 3xTF32 (tcgen05.mma.kind::tf32, fp32 accumulate in tensor memory; relative error ~1e-6 like an
+ * fp32 FMA chain).  Replaces the cuBLAS SIMT sgemm calls behind the reference's nn.Linear / F.linear sites of
+ * the decoder layer (mmcv FFN / MultiheadAttention projections, deform3d_cross_attn.py:211-212,326,
+ * detr3d_head.py:72-95) and their autograd.
+ *   a_mn_major = 0: A is (M,K) row-major with row stride lda      (x in x.W^T; dY in dY.W)
+ *   a_mn_major = 1: A is (K,M) row-major with row stride lda      (dY in dY^T.X)
+ *   b_mn_major = 0: B is (N,K) row-major with row stride ldb      (W in x.W^T)
+ *   b_mn_major = 1: B is (K,N) row-major with row stride ldb      (W in dY.W; X in dY^T.X)
+ * C is (M,N) row-major with row stride ldc.  batch > 1: operand b of the batch starts stride_* floats further.
+ * A, B 16-byte aligned; lda, ldb, stride_a, stride_b and each operand's contiguous extent multiples of 4
+ * (else GD4D_ERR_ALIGN / GD4D_ERR_UNSUPPORTED: the caller keeps its library GEMM for such shapes). */
+GD4D_API int gd4d_gemm_tf32x3(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
+                              int32_t b_mn_major, float* C, int64_t ldc, const float* bias, int32_t relu, int32_t M,
+                              int32_t N, int32_t K, int32_t batch, int64_t stride_a, int64_t stride_b,
+                              int64_t stride_c, void* cuda_stream);
+
+/* Exact-fp32 (FFMA) GEMM for the small-M shapes of the decoder layer (csrc/sgemm_small.cu): same contract and
+ * argument meaning as gd4d_gemm_tf32x3.  The default for M = B*Q = 900: a tcgen05.mma.kind::tf32 costs 153 cycles
+ * whatever its N (tools/umma_latency.cu), so 8 row tiles of 128 cannot beat a register-tiled SIMT kernel there. */
+GD4D_API int gd4d_sgemm_small(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
+                              int32_t b_mn_major, float* C, int64_t ldc, const float* bias, int32_t relu, int32_t M,
+                              int32_t N, int32_t K, int32_t batch, int64_t stride_a, int64_t stride_b,
+                              int64_t stride_c, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
