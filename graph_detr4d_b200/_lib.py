@@ -39,6 +39,7 @@ EXPORTS = (
     "gd4d_add_layernorm_bwd",
     "gd4d_adamw_chunk",
     "gd4d_adamw_multi",
+    "gd4d_softmax_bwd",
     "gd4d_gemm_tf32x3",
     "gd4d_sgemm_small",
     # include/gd4d_frustum.h
@@ -151,6 +152,7 @@ def load(build_if_missing: bool = True):
                 ("gd4d_add_layernorm_bwd", [vp] * 9 + [i64, i32, i32, vp]),
                 ("gd4d_adamw_chunk", []),
                 ("gd4d_adamw_multi", [vp, vp, i32, vp, f32, f32, f32, f32, f32, vp]),
+                ("gd4d_softmax_bwd", [vp, vp, vp, i64, i32, vp]),
                 ("gd4d_gemm_tf32x3", [vp, i64, i32, vp, i64, i32, vp, i64, vp, i32, i32, i32, i32, i32, i64, i64, i64, vp]),
                 ("gd4d_sgemm_small", [vp, i64, i32, vp, i64, i32, vp, i64, vp, i32, i32, i32, i32, i32, i64, i64, i64, vp]),
                 ("gd4d_frustum_pe", [vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32,

@@ -204,6 +204,40 @@ add_layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int launched() { return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA; }
 
+// Softmax backward over the last dim, one warp per row, ONE pass: ds = p * (g - sum_j g_j p_j).
+// (ATen materialises g * p first -- a 26 MB elementwise pass per decoder layer at 8 x 900 x 900 -- and
+// then runs its warp kernel over that and p.)  Up to 1024 columns; in place over g allowed.
+template <int VPL>   // float4 per lane
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ p,
+                                                          float* __restrict__ ds, int64_t rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* g4 = reinterpret_cast<const float4*>(g + row * cols);
+  const float4* p4 = reinterpret_cast<const float4*>(p + row * cols);
+  float4* d4 = reinterpret_cast<float4*>(ds + row * cols);
+  const int n4 = cols >> 2;
+  float4 gv[VPL], pv[VPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int j = i * 32 + lane;
+    gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pv[i] = gv[i];
+    if (j < n4) { gv[i] = g4[j]; pv[i] = __ldg(p4 + j); }
+    sum += gv[i].x * pv[i].x + gv[i].y * pv[i].y + gv[i].z * pv[i].z + gv[i].w * pv[i].w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n4)
+      d4[j] = make_float4(pv[i].x * (gv[i].x - sum), pv[i].y * (gv[i].y - sum), pv[i].z * (gv[i].z - sum),
+                          pv[i].w * (gv[i].w - sum));
+  }
+}
+
 }  // namespace gd4d
 
 extern "C" {
@@ -312,6 +346,20 @@ int gd4d_add_layernorm_bwd(const float* gy, const float* gy2, const float* s, co
     default: GD4D_LN_BWD(8); break;
   }
 #undef GD4D_LN_BWD
+  return gd4d::launched();
+}
+
+int gd4d_softmax_bwd(const float* grad_out, const float* probs, float* grad_in, int64_t rows, int32_t cols,
+                     void* cuda_stream) {
+  if (grad_out == nullptr || probs == nullptr || grad_in == nullptr) return GD4D_ERR_NULL;
+  if (rows <= 0 || cols <= 0 || cols % 4 != 0 || cols > 1024 || rows > (1LL << 34)) return GD4D_ERR_DIMS;
+  if (!gd4d::al16(grad_out) || !gd4d::al16(probs) || !gd4d::al16(grad_in)) return GD4D_ERR_ALIGN;
+  auto st = static_cast<cudaStream_t>(cuda_stream);
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  const int n4 = cols / 4;
+  if (n4 <= 64) gd4d::softmax_bwd_kernel<2><<<grid, 256, 0, st>>>(grad_out, probs, grad_in, rows, cols);
+  else if (n4 <= 128) gd4d::softmax_bwd_kernel<4><<<grid, 256, 0, st>>>(grad_out, probs, grad_in, rows, cols);
+  else gd4d::softmax_bwd_kernel<8><<<grid, 256, 0, st>>>(grad_out, probs, grad_in, rows, cols);
   return gd4d::launched();
 }
 

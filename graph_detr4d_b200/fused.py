@@ -99,6 +99,27 @@ def bias_act_(y: torch.Tensor, bias: torch.Tensor, relu: bool = True) -> torch.T
     return y
 
 
+def softmax_bwd_(grad: torch.Tensor, probs: torch.Tensor) -> torch.Tensor:
+    """In place over ``grad``: softmax backward along the last dim, one launch, one pass (ATen: g * p as its
+    own elementwise pass, then its kernel).  Contiguous fp32, last dim % 4 == 0 and <= 1024."""
+    _require_cuda(grad, "grad")
+    cols = grad.shape[-1]
+    st = _lib.load().gd4d_softmax_bwd(grad.data_ptr(), probs.data_ptr(), grad.data_ptr(), grad.numel() // cols, cols,
+                                      _stream_ptr(grad.device))
+    _lib.check(st, "gd4d_softmax_bwd")
+    _count()
+    return grad
+
+
+SOFTMAX_BWD = True     # A/B switch (tools/ab_step.py)
+
+
+def can_fuse_softmax_bwd(grad: torch.Tensor, probs: torch.Tensor) -> bool:
+    return (ENABLED and SOFTMAX_BWD and grad.is_cuda and grad.dtype == probs.dtype == torch.float32 and grad.is_contiguous()
+            and probs.is_contiguous() and grad.shape == probs.shape and grad.shape[-1] % 4 == 0
+            and grad.shape[-1] <= 1024 and grad.data_ptr() % 16 == 0 and probs.data_ptr() % 16 == 0)
+
+
 class _AddLayerNormFn(torch.autograd.Function):
     """y = [relu](LayerNorm(x + xbias + r1 + r2)); gamma/beta gradients go through DeferredWgrad
     when it is active (one batched reduction per step), else they are reduced here.  ``xbias``

@@ -432,7 +432,12 @@ class _AttnCoreFn(torch.autograd.Function):
         vv = v.reshape(L, B * H, d).transpose(0, 1)
         dv = torch.empty_like(v)
         torch.bmm(attn.transpose(1, 2), gg, out=dv.view(L, B * H, d).transpose(0, 1))
-        ds = torch._softmax_backward_data(torch.bmm(gg, vv.transpose(1, 2)), attn, -1, attn.dtype)
+        from . import fused
+        ds = torch.bmm(gg, vv.transpose(1, 2))
+        if fused.can_fuse_softmax_bwd(ds, attn):
+            fused.softmax_bwd_(ds, attn)                                  # one pass, in place
+        else:
+            ds = torch._softmax_backward_data(ds, attn, -1, attn.dtype)
         dqk = torch.empty_like(qk)
         z = _zero(qk)
         torch.baddbmm(z, ds, k, beta=0.0, alpha=ctx.alpha,

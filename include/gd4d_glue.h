@@ -90,6 +90,12 @@ GD4D_API int gd4d_adamw_multi(const gd4d_adamw_tensor* table_dev, const int32_t*
                               int32_t n_blocks, const float* step_dev, float lr, float beta1,
                               float beta2, float eps, float weight_decay, void* cuda_stream);
 
+/* Softmax backward over the last dim in one pass: grad_in = probs * (grad_out - sum_j grad_out_j probs_j).
+ * rows x cols fp32, cols % 4 == 0, cols <= 1024, 16-byte aligned; grad_in may alias grad_out.  The softmax of
+ * the decoder layer's self-attention (mmcv MultiheadAttention -> nn.MultiheadAttention, 8 x 900 x 900 per layer). */
+GD4D_API int gd4d_softmax_bwd(const float* grad_out, const float* probs, float* grad_in, int64_t rows, int32_t cols,
+                              void* cuda_stream);
+
 /* fp32-accurate GEMM on the tensor cores (csrc/gemm_tf32x3.cu): C[M,N] = A . B^T (+ bias[N]) (relu), error-
  * compensated 3xTF32 (tcgen05.mma.kind::tf32, fp32 accumulate in tensor memory; relative error ~1e-6 like an
  * fp32 FMA chain).  Replaces the cuBLAS SIMT sgemm calls behind the reference's nn.Linear / F.linear sites of

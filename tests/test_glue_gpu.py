@@ -252,3 +252,17 @@ def test_add_layernorm_second_output_with_pos(use):
         else:
             assert _rel(pg.grad, po.grad) <= TOL
         assert _rel(lng.weight.grad, ln.weight.grad) <= 5e-5 and _rel(lng.bias.grad, ln.bias.grad) <= 5e-5
+
+
+@pytest.mark.parametrize("rows,cols", [(8 * 900, 900), (37, 64), (5, 1024), (3, 4)])
+def test_one_pass_softmax_backward_matches_aten(rows, cols):
+    """gd4d_softmax_bwd (in place over the incoming gradient) vs torch._softmax_backward_data."""
+    from graph_detr4d_b200 import fused
+    g = torch.Generator().manual_seed(rows + cols)
+    p = torch.randn(rows, cols, generator=g).cuda().softmax(-1)
+    go = torch.randn(rows, cols, generator=g).cuda()
+    want = torch._softmax_backward_data(go, p, -1, p.dtype)
+    assert fused.can_fuse_softmax_bwd(go, p)
+    got = fused.softmax_bwd_(go.clone(), p)
+    assert _rel(got, want.cpu()) <= 2e-6
+    assert not fused.can_fuse_softmax_bwd(go[:, :cols - 1], p[:, :cols - 1])     # ragged / strided: ATen path

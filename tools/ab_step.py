@@ -21,9 +21,10 @@ def build(name):
     fused.ENABLED = name != "no_fused"
     modules._PACKED_GEN = name != "no_gen"
     graphed.MULTI_TENSOR_ADAMW = name != "no_adamw"
+    fused.SOFTMAX_BWD = name != "no_smbwd"
     model = copy.deepcopy(base_model)
     st = GraphedTrainStep(model, lambda f: bench.loss_fn(*(lambda s, _, r: (s, r))(*model(f, metas, 1))), feats, metas)
-    fused.ENABLED, modules._PACKED_GEN, graphed.MULTI_TENSOR_ADAMW = True, True, True
+    fused.ENABLED, modules._PACKED_GEN, graphed.MULTI_TENSOR_ADAMW, fused.SOFTMAX_BWD = True, True, True, True
     return st
 
 
