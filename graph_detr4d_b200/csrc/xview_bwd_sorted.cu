@@ -36,8 +36,8 @@ struct SortedWs {
   int* row_start;       // R    block-local exclusive prefix
   int* block_sums;      // nblk exclusive prefix of the 2048-row block totals
   int* base;            // B*Q*Hh  first cid of each (b,q,head)
-  int4* rec;            // cap  {row | -1, rank, grad_out row, coef bits}
-  int4* sorted;         // cap  {row, grad_out row, coef bits, cid}
+  int4* rec;            // cap  32-byte records (two int4): {value row ptr, grad-map row ptr | go_row, coef, row | -1, rank}
+  int4* sorted;         // cap  32-byte SRec records (two int4 each), ordered by pixel row
   float* dots;          // cap  value_row . grad_out_row per contribution
   long long level_row0[GD4D_MAX_LEVELS + 1];   // first global row of each level (+ total)
   int R, nblk;
@@ -61,7 +61,7 @@ static long long ws_layout(const gd4d_xview_params& p, SortedWs* ws, char* base_
   auto take = [&](long long bytes) { const long long o = off; off += (bytes + 255) / 256 * 256; return o; };
   const long long o_cnt = take(16), o_rc = take(R * 4), o_rs = take(R * 4), o_bs = take(nblk * 4);
   const long long o_base = take(static_cast<long long>(p.B) * p.Q * p.Hh * 4);
-  const long long o_rec = take(cap * 16), o_sorted = take(cap * 16), o_dots = take(cap * 4);
+  const long long o_rec = take(cap * 32), o_sorted = take(cap * 32), o_dots = take(cap * 4);
   if (ws) {
     ws->level_row0[p.L] = R;
     ws->R = static_cast<int>(R); ws->nblk = static_cast<int>(nblk); ws->cap = cap;
@@ -133,14 +133,20 @@ xview_bwd_items_kernel(const __grid_constant__ gd4d_xview_params p, const __grid
       const int cid0 = base + item * 4;
       if (!FINISH) {
         const float cw[4] = {r.wt * r.w00, r.wt * r.w01, r.wt * r.w10, r.wt * r.w11};
+        const VT* vbase = static_cast<const VT*>(p.value[l]);
+        float* gbase = p.grad_value[l];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          int4 rec = make_int4(-1, 0, 0, 0);
+          int4 lo = make_int4(0, 0, 0, 0), hi = make_int4(0, 0, -1, 0);
           if (o[j] != z) {                                       // in-map corner
             const int row = static_cast<int>(ws.level_row0[l] + o[j] / p.C);
-            rec = make_int4(row, atomicAdd(ws.row_count + row, 1), go_row, __float_as_int(cw[j]));
+            const unsigned long long vp = reinterpret_cast<unsigned long long>(vbase + o[j]);
+            const unsigned long long gp = gbase != nullptr ? reinterpret_cast<unsigned long long>(gbase + o[j]) : 0ull;
+            lo = make_int4(static_cast<int>(vp), static_cast<int>(vp >> 32), static_cast<int>(gp), static_cast<int>(gp >> 32));
+            hi = make_int4(go_row, __float_as_int(cw[j]), row, atomicAdd(ws.row_count + row, 1));
           }
-          ws.rec[cid0 + j] = rec;
+          ws.rec[2 * (cid0 + j)] = lo;
+          ws.rec[2 * (cid0 + j) + 1] = hi;
         }
       } else {
         float d[4];
@@ -280,130 +286,197 @@ __global__ void __launch_bounds__(256) xview_bwd_scan_kernel(const SortedWs ws) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: scatter every contribution to its sorted position
+// K3: scatter every contribution record (K1 already resolved its value-row pointer, grad-map row pointer --
+//     NULL when no feature gradient is wanted -- grad_out row and coefficient) to its sorted position, adding
+//     its cid.  Also returns the histogram entries to zero for the next call.
 // ------------------------------------------------------------------------------------------------
+struct __align__(16) SRec {
+  const void* vrow;   // value row of this contribution's pixel
+  float* gvrow;       // grad-map row (fp32), or NULL
+  int go_row;         // grad_out row (b, head, q)
+  float coef;         // wt * bilinear corner weight
+  int cid;            // where its dot product goes
+  int row;            // global pixel row (run key)
+};
+static_assert(sizeof(SRec) == 32, "two 16-byte halves per record");
+
 __global__ void __launch_bounds__(256) xview_bwd_scatter_kernel(const SortedWs ws) {
   const unsigned n = ws.counters[0];
   for (unsigned cid = blockIdx.x * blockDim.x + threadIdx.x; cid < n; cid += gridDim.x * blockDim.x) {
-    const int4 r = ws.rec[cid];
-    if (r.x < 0) continue;
-    const int pos = ws.row_start[r.x] + ws.block_sums[r.x / kScanBlock] + r.y;
-    ws.sorted[pos] = make_int4(r.x, r.z, r.w, static_cast<int>(cid));
+    const int4 hi = ws.rec[2 * cid + 1];                               // {go_row, coef, row | -1, rank}
+    if (hi.z < 0) continue;
+    const int4 lo = ws.rec[2 * cid];
+    const int pos = ws.row_start[hi.z] + ws.block_sums[hi.z / kScanBlock] + hi.w;
+    ws.sorted[2 * pos] = lo;
+    ws.sorted[2 * pos + 1] = make_int4(hi.x, hi.y, static_cast<int>(cid), hi.z);   // SRec: go_row, coef, cid, row
+    if (hi.w == 0) ws.row_count[hi.z] = 0;                             // one writer per row (K2 was the last reader)
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: owner pass
+// K4: owner pass.  A warp owns 32 consecutive sorted contributions (one record per lane, fields broadcast by
+// shuffle), processed 4 at a time:
+//   * value rows are fetched at run starts only, by cp.async into a per-warp shared-memory ring, one batch
+//     AHEAD (no registers, no stall at a run start even where every contribution is its own run: level 0)
+//   * the batch's 4 grad_out rows (L2-resident, 7 MB) are register gathers issued back to back
+//   * per contribution: dot(value row, g) and acc += coef * g; the 4 dots are reduced together (butterfly
+//     with halving payload: 6 shuffles per batch instead of 20) and lane u stores dot u
+//   * at a run end the row's gradient leaves with one red.global.add.v4.f32 per lane vector
 // ------------------------------------------------------------------------------------------------
-// retire one run: the row's feature gradient leaves with ONE vector reduction per lane vector
-template <typename VT, int NV>
-__device__ __forceinline__ void flush_row(const gd4d_xview_params& p, const SortedWs& ws, int row,
-                                          const float (&acc)[Slice<VT>::VEC * NV], int lane) {
-  constexpr int VEC = Slice<VT>::VEC;
-  constexpr int GV = VEC / 4;
-  if (row < 0) return;
-  int l = 0;
-  while (l + 1 < p.L && row >= ws.level_row0[l + 1]) ++l;
-  if (lane == 0) ws.row_count[row] = 0;                            // histogram ready for the next call
-  float* gv = p.grad_value[l];
-  if (gv == nullptr) return;
-  gv += (static_cast<long long>(row) - ws.level_row0[l]) * p.C;
-#pragma unroll
-  for (int j = 0; j < NV; ++j)
-#pragma unroll
-    for (int k = 0; k < GV; ++k) {
-      const int ch = (j * 32 + lane) * VEC + k * 4;
-      red_add_v4(gv + ch, acc[j * VEC + k * 4], acc[j * VEC + k * 4 + 1], acc[j * VEC + k * 4 + 2],
-                 acc[j * VEC + k * 4 + 3]);
-    }
-}
+constexpr int kOwnerWarps = 8;
+constexpr int kOwnerU = 4;             // contributions per batch
+constexpr int kOwnerSlots = 2 * kOwnerU;   // value-row ring: the current batch's and the next batch's run starts
 
 template <typename VT, int NV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kOwnerWarps * 32, 2)
 xview_bwd_owner_kernel(const __grid_constant__ gd4d_xview_params p, const __grid_constant__ SortedWs ws) {
   constexpr int VEC = Slice<VT>::VEC;     // channels per 16-byte value load
   constexpr int PL = VEC * NV;            // channels per lane
-  constexpr int GV = VEC / 4;             // float4 per value vector in the fp32 grad_out / grad map rows
-  constexpr int U = PL > 8 ? 2 : 4;       // contributions in flight (16-channel lanes: 2, or the batch spills)
-  const int lane = threadIdx.x & 31;
+  constexpr int GV = VEC / 4;             // float4 per value vector in the fp32 grad_out / grad-map rows
+  constexpr int U = kOwnerU;
+  constexpr int kRowBytes = 512 * NV;     // one value row (C * sizeof(VT))
+  extern __shared__ __align__(16) unsigned char ring_all[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char* ring = ring_all + wid * (kOwnerSlots * kRowBytes);
+  const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring));
   const int n = static_cast<int>(ws.counters[1]);
   const int nchunks = (n + 31) / 32;
-  const int warps = gridDim.x * kWarpsPerCta;
+  const int warps = gridDim.x * kOwnerWarps;
+  const SRec* sorted = reinterpret_cast<const SRec*>(ws.sorted);
 
-  for (int c = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); c < nchunks; c += warps) {
-    float acc[PL];
-#pragma unroll
-    for (int i = 0; i < PL; ++i) acc[i] = 0.f;
-    float vprev[PL];
-#pragma unroll
-    for (int i = 0; i < PL; ++i) vprev[i] = 0.f;
-    int prev_row = -1;
-
+  for (int c = blockIdx.x * kOwnerWarps + wid; c < nchunks; c += warps) {
     const int i0 = c * 32;
     const int cnt = min(32, n - i0);
-    for (int u0 = 0; u0 < cnt; u0 += U) {
-      int4 rc[U];
-      bool ok[U], start[U];
-      uint4 vraw[U][NV];
-      float4 graw[U][NV][GV];
+    // one record per lane
+    SRec me;
+    me.vrow = nullptr; me.gvrow = nullptr; me.go_row = 0; me.coef = 0.f; me.cid = 0; me.row = -1;
+    if (lane < cnt) {
+      const int4 lo = __ldg(reinterpret_cast<const int4*>(sorted + i0 + lane));
+      const int4 hi = __ldg(reinterpret_cast<const int4*>(sorted + i0 + lane) + 1);
+      me.vrow = reinterpret_cast<const void*>((static_cast<unsigned long long>(static_cast<unsigned>(lo.y)) << 32) |
+                                              static_cast<unsigned>(lo.x));
+      me.gvrow = reinterpret_cast<float*>((static_cast<unsigned long long>(static_cast<unsigned>(lo.w)) << 32) |
+                                          static_cast<unsigned>(lo.z));
+      me.go_row = hi.x; me.coef = __int_as_float(hi.y); me.cid = hi.z; me.row = hi.w;
+    }
+    const int prev = __shfl_up_sync(0xffffffffu, me.row, 1);
+    const unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && (lane == 0 || me.row != prev));
+
+    // value rows of the run starts inside [u0, u0+U) -> ring slots (u0 / U & 1) * U + (i - u0); one commit per batch
+    auto prefetch = [&](int u0) {
+      if (u0 < cnt) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        ok[u] = u0 + u < cnt;
-        rc[u] = ok[u] ? __ldg(ws.sorted + i0 + u0 + u) : make_int4(-1, 0, 0, 0);   // warp-uniform load
-        const int before = (u == 0) ? prev_row : rc[u - 1].x;
-        start[u] = ok[u] && rc[u].x != before;
-        int l = 0;
-        while (l + 1 < p.L && rc[u].x >= ws.level_row0[l + 1]) ++l;
-        const VT* vrow = static_cast<const VT*>(p.value[l]) +
-                         (static_cast<long long>(max(rc[u].x, 0)) - ws.level_row0[l]) * p.C;
-        const float* grow = p.grad_out + static_cast<long long>(rc[u].y) * p.C;
+        for (int u = 0; u < U; ++u) {
+          const int i = u0 + u;
+          if ((starts >> i) & 1u) {                                     // warp-uniform
+            const unsigned long long vp = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(me.vrow), i);
+            const uint32_t dst = ring_s + (((u0 / U) & 1) * U + u) * kRowBytes;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int ch = (j * 32 + lane) * VEC;
-          vraw[u][j] = ldg_nc_v4(vrow + ch, start[u]);             // run starts only
-#pragma unroll
-          for (int k = 0; k < GV; ++k) {
-            const uint4 t = ldg_nc_v4(grow + ch + k * 4, ok[u]);
-            graw[u][j][k] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z),
-                                        __uint_as_float(t.w));
+            for (int j = 0; j < NV; ++j)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (j * 32 + lane) * 16),
+                           "l"(vp + (j * 32 + lane) * 16) : "memory");
           }
         }
       }
-      float dot[U];
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float acc[PL], v[PL];
+#pragma unroll
+    for (int i = 0; i < PL; ++i) { acc[i] = 0.f; v[i] = 0.f; }
+    unsigned long long cur_gv = 0;           // grad-map row of the open run (0: none / not wanted)
+    bool open = false;
+
+    auto flush = [&]() {
+      if (open && cur_gv != 0) {
+        float* gv = reinterpret_cast<float*>(cur_gv);
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+          for (int k = 0; k < GV; ++k)
+            red_add_v4(gv + (j * 32 + lane) * VEC + k * 4, acc[j * VEC + k * 4], acc[j * VEC + k * 4 + 1],
+                       acc[j * VEC + k * 4 + 2], acc[j * VEC + k * 4 + 3]);
+      }
+    };
+
+    prefetch(0);
+    for (int u0 = 0; u0 < cnt; u0 += U) {
+      prefetch(u0 + U);                                                  // next batch's value rows
+      // this batch's grad_out rows
+      float4 g[U][NV][GV];
+      float coef[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (start[u]) {                                            // warp-uniform
-          flush_row<VT, NV>(p, ws, prev_row, acc, lane);
-#pragma unroll
-          for (int i = 0; i < PL; ++i) acc[i] = 0.f;
-#pragma unroll
-          for (int j = 0; j < NV; ++j) Slice<VT>::unpack(vraw[u][j], vprev + j * VEC);
-          prev_row = rc[u].x;
-        }
-        const float coef = __int_as_float(rc[u].z);
-        float d = 0.f;
+        const int i = min(u0 + u, 31);
+        const int go = __shfl_sync(0xffffffffu, me.go_row, i);
+        coef[u] = __shfl_sync(0xffffffffu, me.coef, i);                  // 0 for lanes past cnt
+        const float* grow = p.grad_out + static_cast<long long>(go) * p.C;
 #pragma unroll
         for (int j = 0; j < NV; ++j)
 #pragma unroll
           for (int k = 0; k < GV; ++k) {
-            const float4 g = graw[u][j][k];
-            const int b = j * VEC + k * 4;
-            d = fmaf(vprev[b], g.x, d);     d = fmaf(vprev[b + 1], g.y, d);
-            d = fmaf(vprev[b + 2], g.z, d); d = fmaf(vprev[b + 3], g.w, d);
-            acc[b] = fmaf(coef, g.x, acc[b]);         acc[b + 1] = fmaf(coef, g.y, acc[b + 1]);
-            acc[b + 2] = fmaf(coef, g.z, acc[b + 2]); acc[b + 3] = fmaf(coef, g.w, acc[b + 3]);
+            const uint4 t = ldg_nc_v4_all(reinterpret_cast<const char*>(grow + (j * 32 + lane) * VEC + k * 4));
+            g[u][j][k] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z),
+                                     __uint_as_float(t.w));
           }
-        dot[u] = d;
       }
+      asm volatile("cp.async.wait_group 1;" ::: "memory");              // this batch's value rows have landed
+      __syncwarp();
+      float dot[U];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+      for (int u = 0; u < U; ++u) {
+        const int i = u0 + u;
+        if ((starts >> i) & 1u) {                                       // warp-uniform: a new run
+          flush();
+          cur_gv = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(me.gvrow), i);
+          open = true;
+          const unsigned char* slot = ring + (((u0 / U) & 1) * U + u) * kRowBytes;
 #pragma unroll
-        for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+          for (int j = 0; j < NV; ++j) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(slot + (j * 32 + lane) * 16);
+            Slice<VT>::unpack(raw, v + j * VEC);
+          }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (ok[u] && lane == u) ws.dots[rc[u].w] = dot[u];
+          for (int q = 0; q < PL; ++q) acc[q] = 0.f;
+        }
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+          for (int k = 0; k < GV; ++k) {
+            const float4 gg = g[u][j][k];
+            const int b = j * VEC + k * 4;
+            d0 = fmaf(v[b], gg.x, d0);     d1 = fmaf(v[b + 1], gg.y, d1);
+            d0 = fmaf(v[b + 2], gg.z, d0); d1 = fmaf(v[b + 3], gg.w, d1);
+            acc[b] = fmaf(coef[u], gg.x, acc[b]);         acc[b + 1] = fmaf(coef[u], gg.y, acc[b + 1]);
+            acc[b + 2] = fmaf(coef[u], gg.z, acc[b + 2]); acc[b + 3] = fmaf(coef[u], gg.w, acc[b + 3]);
+          }
+        dot[u] = d0 + d1;
+      }
+      __syncwarp();                                                      // the ring slots of this batch are free again
+      // 4 dots x 32 lanes -> lane u holds dot u: halve the payload at each of the first two butterfly steps
+      {
+        const bool up16 = (lane & 16) != 0;
+        float s0 = up16 ? dot[0] : dot[2], s1 = up16 ? dot[1] : dot[3];          // send the pair the partner keeps
+        float k0 = up16 ? dot[2] : dot[0], k1 = up16 ? dot[3] : dot[1];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);                              // lanes <16: dots 0,1; >=16: dots 2,3
+        const bool up8 = (lane & 8) != 0;
+        const float s = up8 ? k0 : k1;
+        float k = up8 ? k1 : k0;                                                 // bit 3 picks the odd dot of the pair
+        k += __shfl_xor_sync(0xffffffffu, s, 8);
+        k += __shfl_xor_sync(0xffffffffu, k, 4);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        // lane's dot index: 2 * bit4 + bit3; lanes 0, 8, 16, 24 write dots 0..3
+        const int u = ((lane >> 4) << 1) | ((lane >> 3) & 1);
+        const int cid = __shfl_sync(0xffffffffu, me.cid, min(u0 + u, 31));
+        if ((lane & 7) == 0 && u0 + u < cnt) ws.dots[cid] = k;
+      }
     }
-    flush_row<VT, NV>(p, ws, prev_row, acc, lane);
+    flush();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
   }
 }
 
@@ -436,9 +509,18 @@ static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const 
   if (g1 <= 0 || g5 <= 0) return GD4D_ERR_CUDA;
   emit<<<g1, block, smem, stream>>>(p, ws, g.cand_cap);
   xview_bwd_scan_kernel<<<ws.nblk, 256, 0, stream>>>(ws);
-  xview_bwd_scatter_kernel<<<sms * 4, 256, 0, stream>>>(ws);
-  if (g.nv == 1) xview_bwd_owner_kernel<VT, 1><<<sms * 2, block, 0, stream>>>(p, ws);
-  else xview_bwd_owner_kernel<VT, 2><<<sms * 2, block, 0, stream>>>(p, ws);
+  xview_bwd_scatter_kernel<<<sms * 16, 256, 0, stream>>>(ws);
+  {
+    const int osmem = kOwnerWarps * kOwnerSlots * 512 * g.nv;          // per-warp value-row rings
+    auto own1 = xview_bwd_owner_kernel<VT, 1>;
+    auto own2 = xview_bwd_owner_kernel<VT, 2>;
+    if (osmem > 48 * 1024) {
+      if (cudaFuncSetAttribute(g.nv == 1 ? own1 : own2, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem) != cudaSuccess)
+        return GD4D_ERR_CUDA;
+    }
+    if (g.nv == 1) own1<<<sms * 2, kOwnerWarps * 32, osmem, stream>>>(p, ws);
+    else own2<<<sms * 2, kOwnerWarps * 32, osmem, stream>>>(p, ws);
+  }
   finish<<<g5, block, smem, stream>>>(p, ws, g.cand_cap);
   return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
 }

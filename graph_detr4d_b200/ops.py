@@ -24,12 +24,16 @@ __all__ = ["XViewConfig", "GenLayout", "pack_features", "PackedFeatures", "xview
 DYNAMIC_SCHEDULE = True   # persistent grid + work counter (False: one warp per item, static)
 TMA_FORWARD = False       # wide forward through the cp.async.bulk staging path (xview_fwd_tma.cu)
 L2_PREFETCH = os.environ.get("GD4D_L2_PREFETCH", "0") != "0"   # prefetch.global.L2 of the next batch's rows
-# wide backward, opt-in (GD4D_SORTED_BWD=1): sort the corner contributions by pixel row, one warp owns a run
-# (xview_bwd_sorted.cu, 5 launches) instead of one vector reduction per corner read (xview_bwd.cu, 1 launch).
-# Measured r2 (profiles/r2_bwd_variants.json): it cuts the DRAM+L2-atomic traffic as designed (owner kernel
-# 274 MB DRAM, 110 k reductions instead of 486 k) but its first version is instruction-bound (132 warp
-# instructions per contribution) and 199 us vs 141 us end to end at N = 6 -- so the atomics kernel stays default.
-SORTED_BACKWARD = os.environ.get("GD4D_SORTED_BWD", "0") != "0"
+# Wide backward: two implementations behind gd4d_xview_backward.
+#   atomics (xview_bwd.cu, 1 launch): one 1 KB vector reduction per corner read into the shared grad map
+#   sorted  (xview_bwd_sorted.cu, 5 launches): corner contributions sorted by pixel row, one warp owns a run:
+#           value row read once, one reduction per run (486 k -> ~110 k reductions at N = 6)
+# Measured r2 (profiles/r2_bwd_variants.json, bench layer-0 inputs): fp32 N = 6: 154 vs 140 us (the sort's fixed
+# cost -- emit 26 + scan 6 + scatter 11 + finish 27 us -- eats the owner pass's gain), fp32 N = 12: 245 vs 270 us,
+# bf16 N = 12: 271 vs 243 us.  "auto" therefore takes the sorted path for fp32 maps with >= 12 camera images.
+# GD4D_SORTED_BWD=0 / 1 forces one of them.
+_SORTED_ENV = os.environ.get("GD4D_SORTED_BWD", "auto")
+SORTED_BACKWARD = {"0": False, "1": True}.get(_SORTED_ENV, "auto")
 _LAUNCHES = 0      # kernels of libgd4d_xview.so launched by this process (bench: gpu_launches)
 
 
@@ -77,7 +81,12 @@ def _attach_bwd_ws(p: XViewParams, device) -> int:
     """Scratch of the sorted wide backward, one per (device, stream) like the work counter: its
     counters + row histogram are zeroed once here, every launch leaves them zeroed again.
     Returns the number of kernels the backward call will launch."""
-    if not (SORTED_BACKWARD and p.wide and p.mode == MODE_C):
+    if not (p.wide and p.mode == MODE_C):
+        return 1
+    use = SORTED_BACKWARD
+    if use == "auto":
+        use = p.value_dtype == F32 and p.B * p.N >= 12
+    if not use:
         return 1
     need = int(_lib.load().gd4d_xview_bwd_ws_bytes(C.byref(p)))
     if need < 0:

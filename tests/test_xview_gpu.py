@@ -244,7 +244,7 @@ def test_sorted_backward_equals_atomics_backward_and_leaves_its_scratch_clean(dt
             res.setdefault(srt, []).append((gv, small))
         small_only = ops.xview_backward(*args, go, None, grad_wsum=gw)      # no feature gradients wanted
     finally:
-        ops.SORTED_BACKWARD, ops.DYNAMIC_SCHEDULE = False, True
+        ops.SORTED_BACKWARD, ops.DYNAMIC_SCHEDULE = "auto", True
     gv_a, small_a = res[False][0]
     for gv_s, small_s in res[True]:
         for a, b in zip(gv_s, gv_a):

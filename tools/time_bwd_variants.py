@@ -25,5 +25,5 @@ for T, dtype in ((1, "f32"), (2, "f32"), (2, "bf16")):
     torch.cuda.empty_cache()
     if once:
         break
-ops.SORTED_BACKWARD = False
+ops.SORTED_BACKWARD = "auto"
 print(json.dumps(out))
