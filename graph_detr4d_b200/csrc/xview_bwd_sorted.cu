@@ -495,19 +495,12 @@ static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const 
         cudaFuncSetAttribute(finish, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return GD4D_ERR_CUDA;
   }
-  auto items_grid = [&](auto kern) -> int {
-    int grid = g.grid;
-    if (p.sched != nullptr) {   // persistent grid: one resident wave, warps claim work dynamically
-      int occ = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem) != cudaSuccess) return -1;
-      const long long resident = static_cast<long long>(sms) * (occ > 0 ? occ : 1);
-      if (resident < grid) grid = static_cast<int>(resident);
-    }
-    return grid;
-  };
-  const int g1 = items_grid(emit), g5 = items_grid(finish);
-  if (g1 <= 0 || g5 <= 0) return GD4D_ERR_CUDA;
-  emit<<<g1, block, smem, stream>>>(p, ws, g.cand_cap);
+  // emit / finish are chains of dependent round trips (project -> softmax -> records -> atomics), ~17 items on
+  // 32 lanes: a persistent grid claiming work items adds two more round trips per item and leaves most of the
+  // machine's warp slots empty.  One warp per (b, q, head), statically, all of them resident at once.
+  gd4d_xview_params ps = p;
+  ps.sched = nullptr;
+  emit<<<g.grid, block, smem, stream>>>(ps, ws, g.cand_cap);
   xview_bwd_scan_kernel<<<ws.nblk, 256, 0, stream>>>(ws);
   xview_bwd_scatter_kernel<<<sms * 16, 256, 0, stream>>>(ws);
   {
@@ -521,7 +514,7 @@ static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const 
     if (g.nv == 1) own1<<<sms * 2, kOwnerWarps * 32, osmem, stream>>>(p, ws);
     else own2<<<sms * 2, kOwnerWarps * 32, osmem, stream>>>(p, ws);
   }
-  finish<<<g5, block, smem, stream>>>(p, ws, g.cand_cap);
+  finish<<<g.grid, block, smem, stream>>>(ps, ws, g.cand_cap);
   return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
 }
 

@@ -6,7 +6,7 @@ import os, sys, copy
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from graph_detr4d_b200 import synthetic as syn, fused, graphed, modules
+from graph_detr4d_b200 import synthetic as syn, fused, graphed, modules, ops
 from graph_detr4d_b200.graphed import GraphedTrainStep
 
 dev = torch.device("cuda")
@@ -22,9 +22,11 @@ def build(name):
     modules._PACKED_GEN = name != "no_gen"
     graphed.MULTI_TENSOR_ADAMW = name != "no_adamw"
     fused.SOFTMAX_BWD = name != "no_smbwd"
+    ops.SORTED_BACKWARD = {"sorted": True, "atomics": False}.get(name, "auto")
     model = copy.deepcopy(base_model)
     st = GraphedTrainStep(model, lambda f: bench.loss_fn(*(lambda s, _, r: (s, r))(*model(f, metas, 1))), feats, metas)
     fused.ENABLED, modules._PACKED_GEN, graphed.MULTI_TENSOR_ADAMW, fused.SOFTMAX_BWD = True, True, True, True
+    ops.SORTED_BACKWARD = "auto"
     return st
 
 
