@@ -28,10 +28,10 @@ L2_PREFETCH = os.environ.get("GD4D_L2_PREFETCH", "0") != "0"   # prefetch.global
 #   atomics (xview_bwd.cu, 1 launch): one 1 KB vector reduction per corner read into the shared grad map
 #   sorted  (xview_bwd_sorted.cu, 5 launches): corner contributions sorted by pixel row, one warp owns a run:
 #           value row read once, one reduction per run (486 k -> ~110 k reductions at N = 6)
-# Measured r2 (profiles/r2_bwd_variants.json, bench layer-0 inputs): fp32 N = 6: 154 vs 140 us (the sort's fixed
-# cost -- emit 26 + scan 6 + scatter 11 + finish 27 us -- eats the owner pass's gain), fp32 N = 12: 245 vs 270 us,
-# bf16 N = 12: 271 vs 243 us.  "auto" therefore takes the sorted path for fp32 maps with >= 12 camera images.
-# GD4D_SORTED_BWD=0 / 1 forces one of them.
+# Measured r2 (profiles/r2_bwd_variants.json, bench layer-0 inputs, us per backward call, sorted vs atomics):
+# fp32 N = 6: 136 vs 141, fp32 N = 12: 232 vs 271, bf16 N = 12: 254 vs 245; inside the graphed training step
+# (tools/ab_step.py, same process): 4.378 vs 4.448 ms at N = 6, 5.284 vs 5.585 ms at N = 12 (fp32).
+# "auto" therefore takes the sorted path for fp32 maps.  GD4D_SORTED_BWD=0 / 1 forces one of them.
 _SORTED_ENV = os.environ.get("GD4D_SORTED_BWD", "auto")
 SORTED_BACKWARD = {"0": False, "1": True}.get(_SORTED_ENV, "auto")
 _LAUNCHES = 0      # kernels of libgd4d_xview.so launched by this process (bench: gpu_launches)
@@ -85,7 +85,7 @@ def _attach_bwd_ws(p: XViewParams, device) -> int:
         return 1
     use = SORTED_BACKWARD
     if use == "auto":
-        use = p.value_dtype == F32 and p.B * p.N >= 12
+        use = p.value_dtype == F32
     if not use:
         return 1
     need = int(_lib.load().gd4d_xview_bwd_ws_bytes(C.byref(p)))
