@@ -512,10 +512,21 @@ def kernel_roofline(model, feats_dev, metas, T, dtype, dev, reps=300):
             return s.elapsed_time(e) / reps * 1e-3
 
         fwd_prep = [ops.prepare_forward(cfg, s, 1, N, ref, log, off, cam, l2i) for s in sets]
+        sorted_bwd = ops.sorted_backward_active(MODE_C, wide, ops._dtype_code(sets[0][0]))
         bwd_prep = [ops.prepare_backward(cfg, s, 1, N, ref, log, off, cam, l2i, gout, g, grad_wsum=gws)
                     for s, g in zip(sets, gsets)]
         t_f = time_loop(lambda i: fwd_prep[i].launch())
         t_b = time_loop(lambda i: bwd_prep[i].launch())
+        t_b_other = None
+        if wide:                                            # the other backward implementation, for the record
+            keep = ops.SORTED_BACKWARD
+            ops.SORTED_BACKWARD = not sorted_bwd
+            try:
+                other = [ops.prepare_backward(cfg, s, 1, N, ref, log, off, cam, l2i, gout, g, grad_wsum=gws)
+                         for s, g in zip(sets, gsets)]
+                t_b_other = time_loop(lambda i: other[i].launch())
+            finally:
+                ops.SORTED_BACKWARD = keep
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -524,8 +535,8 @@ def kernel_roofline(model, feats_dev, metas, T, dtype, dev, reps=300):
     level_rows = [p["corner_reads"] for p in stats["per_level"]]
     level_bytes = [float(v.numel() * v.element_size()) for v in sets[0]]
 
-    def obj(name, t, key):
-        dram = traffic.get(key)                              # ncu dram__bytes_read+write of THIS kernel
+    def obj(name, t, key, tkey=None):
+        dram = traffic.get(tkey or key)                      # ncu dram__bytes_read+write of THIS kernel / call
         alg8d, uniq, moved = ab[key + "_8d"], ab[key + "_unique"], ab[key]
         o = dict(kernel=name, bound="hbm", unit="GB/s", peak=peak, peak_source=peak_src,
                  us_per_launch=t * 1e6, traffic=dram,
@@ -543,7 +554,24 @@ def kernel_roofline(model, feats_dev, metas, T, dtype, dev, reps=300):
         o["achieved"] = basis / t / 1e9
         o["frac"] = o["achieved"] / peak
         o["frac_basis"] = "measured DRAM traffic" if dram else "unique-footprint lower bound (no ncu capture committed)"
-        if l2p is not None and wide:
+        if key == "bwd" and wide:
+            o["implementation"] = ("sorted owner-computes: 5 launches (emit, scan, scatter, owner, finish), "
+                                   "csrc/xview_bwd_sorted.cu" if sorted_bwd else
+                                   "atomics: 1 launch, one red.global.add.v4.f32 row per corner read, csrc/xview_bwd.cu")
+            if t_b_other is not None:
+                o["us_per_launch_" + ("atomics" if sorted_bwd else "sorted")] = t_b_other * 1e6
+        if l2p is not None and wide and key == "bwd" and sorted_bwd:
+            # sorted backward: grad_out rows gathered per contribution (7 MB source: L2-resident rate), value rows
+            # and reductions once per run (>= distinct rows), everything else small
+            U = stats["unique_rows"]
+            g_b, v_b, r_b = ab["S"] * C * 4.0, U * float(row_bytes), U * C * 4.0
+            roof_us = max(g_b / (l2p["gather"]["l2_resident_24MB"] * 1e9) + v_b / (l2p["gather"]["footprint_142MB"] * 1e9),
+                          r_b / (l2p["red_add_v4_f32"]["footprint_142MB"] * 1e9)) * 1e6
+            o["l2"] = dict(gather_bytes=g_b + v_b, red_bytes=r_b, roof_us=roof_us, frac=roof_us / (t * 1e6),
+                           note="owner pass only (the sort's emit / scan / scatter / finish kernels are latency-bound "
+                                "chains, ~45 % of the call: profiles/r2_bwd_sorted_kernel_times.json); rates from "
+                                "profiles/l2_peaks.json")
+        elif l2p is not None and wide:
             bwd = key == "bwd"
             roof_us = 0.0
             for rows, vb in zip(level_rows, level_bytes):
@@ -567,7 +595,8 @@ def kernel_roofline(model, feats_dev, metas, T, dtype, dev, reps=300):
                                 "kernel's reuse of coarse levels is friendlier than the uniform pattern, so ~1.0 is reachable")
         return o
     tag = "C,wide" if wide else "C,narrow"
-    return obj(f"xview_bwd_kernel<{tag}>", t_b, "bwd"), obj(f"xview_fwd_kernel<{tag}>", t_f, "fwd")
+    bname = f"gd4d_xview_backward<{tag}> (sorted)" if sorted_bwd else f"xview_bwd_kernel<{tag}>"
+    return obj(bname, t_b, "bwd", "bwdS" if sorted_bwd else "bwd"), obj(f"xview_fwd_kernel<{tag}>", t_f, "fwd")
 
 
 if __name__ == "__main__":

@@ -77,16 +77,20 @@ def _sched_ptr(device) -> int:
 _BWD_WS = {}
 
 
+def sorted_backward_active(mode: int, wide: bool, value_dtype_code: int) -> bool:
+    """Which backward gd4d_xview_backward will run for this configuration (see SORTED_BACKWARD)."""
+    if not (wide and mode == MODE_C):
+        return False
+    if SORTED_BACKWARD == "auto":
+        return value_dtype_code == F32
+    return bool(SORTED_BACKWARD)
+
+
 def _attach_bwd_ws(p: XViewParams, device) -> int:
     """Scratch of the sorted wide backward, one per (device, stream) like the work counter: its
     counters + row histogram are zeroed once here, every launch leaves them zeroed again.
     Returns the number of kernels the backward call will launch."""
-    if not (p.wide and p.mode == MODE_C):
-        return 1
-    use = SORTED_BACKWARD
-    if use == "auto":
-        use = p.value_dtype == F32
-    if not use:
+    if not sorted_backward_active(p.mode, bool(p.wide), p.value_dtype):
         return 1
     need = int(_lib.load().gd4d_xview_bwd_ws_bytes(C.byref(p)))
     if need < 0:

@@ -22,10 +22,15 @@ def main(path):
     rd = next(k for k in rows[0] if k.startswith("dram__bytes_read.sum"))
     wr = next(k for k in rows[0] if k.startswith("dram__bytes_write.sum"))
     scale = {"[byte]": 1, "[Kbyte]": 1e3, "[Mbyte]": 1e6, "[Gbyte]": 1e9}
-    acc = collections.defaultdict(list)
+    slots = collections.OrderedDict()                       # a sorted backward call is five kernels: sum its slot
     for r in rows:
         b = float(r[rd]) * scale[rd.split()[-1]] + float(r[wr]) * scale[wr.split()[-1]]
-        acc[r["case"]].append(b)
+        key = (r["case"], r.get("slot", len(slots)))
+        slots[key] = slots.get(key, 0.0) + b
+    acc = collections.defaultdict(list)
+    for (case, _), b in slots.items():
+        if case:
+            acc[case].append(b)
     out = collections.defaultdict(dict)
     for case, vals in acc.items():
         base, direction = case.rsplit("_", 1)

@@ -1,6 +1,7 @@
 """Launch each fused kernel a few times at the flagship shapes (for `ncu --set full`).
-Order of launches (2 each): C-wide fp32 N=6 fwd,bwd | C-wide fp32 N=12 | C-wide bf16 N=12 |
-C-narrow fp32 N=12 | A fp32 N=6."""
+Order of launches (REPS each): per case  fwd, bwd (atomics), and for the wide cases bwdS (sorted: 5 kernels).
+Cases: C-wide fp32 N=6 | C-wide fp32 N=12 | C-wide bf16 N=12 | C-narrow fp32 N=12 | A fp32 N=6.
+tools/summarize_profiles.py full ... <the printed CASES line> names the launches."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -30,11 +31,22 @@ for name, mode, T, dtype, wide in cases:
     gout = torch.randn_like(f.out)
     gws = torch.randn_like(f.wsum) if f.wsum is not None else None
     gv = [torch.zeros(v.shape, device="cuda", dtype=torch.float32) for v in packed.levels]
+    ops.SORTED_BACKWARD = False
     b = ops.prepare_backward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i, gout, gv, gws)
+    bs = None
+    if wide:
+        ops.SORTED_BACKWARD = True
+        bs = ops.prepare_backward(cfg, packed.levels, 1, sc["N"], ref, logits, offsets, cam, l2i, gout, gv, gws)
+    ops.SORTED_BACKWARD = "auto"
     for _ in range(REPS):
         flush.zero_()
         f.launch()
         flush.zero_()
         b.launch()
+        if bs is not None:
+            flush.zero_()
+            bs.launch()
     torch.cuda.synchronize()
     print(name, "done", flush=True)
+print("CASES", " ".join(sum(([n + "_fwd", n + "_bwd"] + ([n + "_bwdS"] if w else []) for n, _, _, _, w in cases
+                             if not only or n in only.split(",")), [])))

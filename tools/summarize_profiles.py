@@ -66,10 +66,31 @@ def full(rep, out, cases):
     idx = [hdr.index(k) for k in KEEP if k in hdr]
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow(["case"] + [f"{hdr[i]} [{units[i]}]" for i in idx])
-        for n, r in enumerate(data):
-            case = cases[n % len(cases)] if cases else ""
-            w.writerow([case] + [r[i][:90] for i in idx])
+        w.writerow(["case", "slot"] + [f"{hdr[i]} [{units[i]}]" for i in idx])
+        # a backward call of the sorted path is five kernels: scan / scatter / owner / finish belong to the
+        # slot their emit kernel (items<.., false>) opened; every other xview kernel opens its own slot.
+        # Slots are named by walking REPS repetitions of each case group (fwd, bwd[, bwdS]) in launch order.
+        ki = hdr.index("Kernel Name")
+        follower = re.compile(r"xview_bwd_(scan|scatter|owner)_kernel|xview_bwd_items_kernel<[^>]*(true|\(bool\)1|, 1)>")
+        groups, i = [], 0
+        while i < len(cases):                                   # [[fwd, bwd], [fwd, bwd, bwdS], ...]
+            j = i + 1
+            while j < len(cases) and cases[j].rsplit("_", 1)[0] == cases[i].rsplit("_", 1)[0]:
+                j += 1
+            groups.append(cases[i:j])
+            i = j
+        slots = -1
+        names = []
+        for r in data:
+            if not follower.search(r[ki]):
+                slots += 1
+            names.append(slots)
+        nslots = slots + 1
+        reps = max(1, nslots // max(1, len(cases)))
+        order = [c for g in groups for _ in range(reps) for c in g] if cases else []
+        for r, sl in zip(data, names):
+            case = order[sl] if sl < len(order) else ""
+            w.writerow([case, sl] + [r[i][:90] for i in idx])
     print(open(out).read()[:3000])
 
 
