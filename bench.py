@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=1, help="temporal frames T of the headline (cameras = 6T)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the T=2 and end-to-end-train legs")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the kernel-alone timing leg (ncu launch-list runs)")
     return ap.parse_args()
 
 
@@ -383,7 +384,7 @@ def main():
 
     # ---- roofline of the dominant hand-written kernel, timed live -------------------------
     roof = roof_fwd = None
-    if D.rank == 0:
+    if D.rank == 0 and not args.no_roofline:
         roof, roof_fwd = kernel_roofline(model, stepper.static_feats, metas, T, dtype, D.dev)
     del stepper, model
     gc.collect()
