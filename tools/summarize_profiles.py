@@ -1,7 +1,7 @@
 """Turn gpurun_out/ ncu artefacts into the small tracked summaries under profiles/.
 
   python tools/summarize_profiles.py launches <launches.csv> <out_prefix>
-  python tools/summarize_profiles.py full <prof.ncu-rep> <out.csv> [case names...]
+  python tools/summarize_profiles.py full <prof.ncu-rep | raw.csv> <out.csv> [case names...]
 """
 import collections
 import csv
@@ -60,7 +60,12 @@ def launches(path, prefix):
 
 
 def full(rep, out, cases):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """``rep``: an .ncu-rep, or the raw CSV already exported next to the GPU (`ncu -i rep --page raw --csv`;
+    a --set full report of 25 kernels is tens of MB, the CSV a few hundred KB)."""
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = [hdr.index(k) for k in KEEP if k in hdr]
