@@ -12,11 +12,13 @@ value    = inputs resident in HBM when the timed region starts
 e2e      = same through the public module API with HOST buffers: the step's feature maps are copied
            H2D from ONE pinned buffer (one copy per step, overlapped with the previous step) and the
            loss is read back D2H inside the timed region
-roofline = the dominant hand-written kernel (fused wide backward), timed live with CUDA events on the
-           launching stream.  `frac` = measured DRAM bytes (ncu capture of this code, profiles/traffic.json)
-           / time / measured HBM peak; beside it the SURVEY 8d algorithmic fraction, the unique-footprint
-           lower bound and the fraction of the MEASURED L2 gather/reduction roof (profiles/l2_peaks.json)
-           that actually bounds the kernel.
+roofline = the dominant hand-written kernel, timed live with CUDA events on the launching stream: the owner pass
+           of the sorted wide backward (fp32 maps; its time = the backward call with it minus the same call
+           without it) with the whole 5-launch backward call nested under `backward_call`; for bf16 maps the
+           one-launch atomics backward.  `frac` = measured DRAM bytes (ncu capture of this code,
+           profiles/traffic.json) / time / measured HBM peak; beside it the algorithmic / SURVEY 8d fraction, the
+           unique-footprint lower bound and the fraction of the MEASURED L2 gather/reduction roof
+           (profiles/l2_peaks.json).
 extras   = the same measurement for the Graph-DETR4D flagship (T = 2 -> 12 cameras) with fp32 and bf16
            feature maps (BASELINE.json configs[2]) and the end-to-end backbone+FPN+decoder training step
            (configs[3], `train_frames_per_s`), so the driver's record holds them too.
@@ -518,6 +520,14 @@ def kernel_roofline(model, feats_dev, metas, T, dtype, dev, reps=300):
                     for s, g in zip(sets, gsets)]
         t_f = time_loop(lambda i: fwd_prep[i].launch())
         t_b = time_loop(lambda i: bwd_prep[i].launch())
+        t_b_noowner = None
+        if sorted_bwd:                                       # owner kernel alone = call with it - call without it
+            from graph_detr4d_b200 import _lib as _l
+            for bp in bwd_prep:
+                bp.params.flags |= _l.FLAG_BWD_SKIP_OWNER
+            t_b_noowner = time_loop(lambda i: bwd_prep[i].launch())
+            for bp in bwd_prep:
+                bp.params.flags &= ~_l.FLAG_BWD_SKIP_OWNER
         t_b_other = None
         if wide:                                            # the other backward implementation, for the record
             keep = ops.SORTED_BACKWARD
@@ -596,8 +606,31 @@ def kernel_roofline(model, feats_dev, metas, T, dtype, dev, reps=300):
                                 "kernel's reuse of coarse levels is friendlier than the uniform pattern, so ~1.0 is reachable")
         return o
     tag = "C,wide" if wide else "C,narrow"
-    bname = f"gd4d_xview_backward<{tag}> (sorted)" if sorted_bwd else f"xview_bwd_kernel<{tag}>"
-    return obj(bname, t_b, "bwd", "bwdS" if sorted_bwd else "bwd"), obj(f"xview_fwd_kernel<{tag}>", t_f, "fwd")
+    bname = f"gd4d_xview_backward<{tag}> (sorted, 5 launches)" if sorted_bwd else f"xview_bwd_kernel<{tag}>"
+    call = obj(bname, t_b, "bwd", "bwdS" if sorted_bwd else "bwd")
+    fwd = obj(f"xview_fwd_kernel<{tag}>", t_f, "fwd")
+    if not (sorted_bwd and t_b_noowner is not None and t_b > t_b_noowner):
+        return call, fwd
+    # The dominant kernel of the sorted call: the owner pass.  Algorithmic bytes: every distinct pixel
+    # row read once (value) and read-modify-written once (fp32 grad map), the grad_out rows once, one 32-byte
+    # record + one 4-byte dot per corner contribution.
+    t_o = t_b - t_b_noowner
+    U, S = stats["unique_rows"], ab["S"]
+    alg = U * float(row_bytes) + 2.0 * U * C * 4 + 1.0 * Q * HEADS * C * 4 + S * 36.0
+    dram = traffic.get("bwdSowner")
+    basis = dram if dram else alg
+    owner = dict(kernel=f"xview_bwd_owner_kernel<{tag}>", bound="hbm", unit="GB/s", peak=peak, peak_source=peak_src,
+                 us_per_launch=t_o * 1e6,
+                 timing=f"live: the backward call with the owner pass minus the same call without it "
+                        f"(GD4D_FLAG_BWD_SKIP_OWNER), {reps} back-to-back launches each, CUDA events on the launch "
+                        f"stream, 3 rotating value-map copies (footprint > L2)",
+                 traffic=dram, traffic_source=call["traffic_source"],
+                 algorithmic_bytes=alg, frac_algorithmic=alg / t_o / 1e9 / peak,
+                 achieved=basis / t_o / 1e9, frac=basis / t_o / 1e9 / peak,
+                 frac_basis="measured DRAM traffic" if dram else "algorithmic bytes (no ncu capture committed)",
+                 corner_contributions=S, unique_rows=U, share_of_backward_call=t_o / t_b,
+                 backward_call=call)
+    return owner, fwd
 
 
 if __name__ == "__main__":

@@ -19,6 +19,7 @@ MODE_A, MODE_C, MODE_V2 = 0, 1, 2
 F32, BF16 = 0, 1
 FLAG_TMA_FORWARD = 1
 FLAG_L2_PREFETCH = 2
+FLAG_BWD_SKIP_OWNER = 4        # measurement only (include/gd4d_xview.h)
 
 EXPORTS = (
     "gd4d_abi_version",

@@ -503,7 +503,7 @@ static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const 
   emit<<<g.grid, block, smem, stream>>>(ps, ws, g.cand_cap);
   xview_bwd_scan_kernel<<<ws.nblk, 256, 0, stream>>>(ws);
   xview_bwd_scatter_kernel<<<sms * 16, 256, 0, stream>>>(ws);
-  {
+  if (!(p.flags & GD4D_FLAG_BWD_SKIP_OWNER)) {
     const int osmem = kOwnerWarps * kOwnerSlots * 512 * g.nv;          // per-warp value-row rings
     auto own1 = xview_bwd_owner_kernel<VT, 1>;
     auto own2 = xview_bwd_owner_kernel<VT, 2>;

@@ -67,6 +67,10 @@ typedef enum gd4d_dtype { GD4D_F32 = 0, GD4D_BF16 = 1 } gd4d_dtype;
 /* forward and backward: prefetch the NEXT batch's corner rows into L2 (prefetch.global.L2) while
  * the current batch's register gathers are in flight */
 #define GD4D_FLAG_L2_PREFETCH 2u
+/* measurement only (bench.py times the owner kernel of the sorted backward as call-with minus call-without):
+ * run the sorted backward WITHOUT its owner pass -- the feature gradient is not produced and the small gradients
+ * are meaningless */
+#define GD4D_FLAG_BWD_SKIP_OWNER 4u
 
 /*
  * One decoder-layer invocation.  All pointers are device pointers.

@@ -31,6 +31,9 @@ def main(path):
     for (case, _), b in slots.items():
         if case:
             acc[case].append(b)
+    for r in rows:                                           # the owner kernel of a sorted backward, on its own
+        if r["case"].endswith("_bwdS") and "xview_bwd_owner_kernel" in r[next(k for k in r if k.startswith("Kernel Name"))]:
+            acc[r["case"] + "owner"].append(float(r[rd]) * scale[rd.split()[-1]] + float(r[wr]) * scale[wr.split()[-1]])
     out = collections.defaultdict(dict)
     for case, vals in acc.items():
         base, direction = case.rsplit("_", 1)
