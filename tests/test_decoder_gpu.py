@@ -196,3 +196,42 @@ def test_training_mode_with_dropout_takes_the_unfused_bias_paths():
     assert not torch.equal(outs[True][0], torch.zeros_like(outs[True][0]))
     for a, b in zip(outs[True], outs[False]):
         assert H.rel_err(a, b) <= 2e-4
+
+
+def test_host_buffer_pipeline_fp16_wire_is_lossless():
+    """The e2e path of bench.py: maps that are fp16-exact (as the reference's fp16 backbone hands them over)
+    travel as fp16 in ONE pinned buffer, are widened by the commit copy, and the step computes on exactly the
+    fp32 values the resident path holds; an fp32 host buffer on the same stepper gives the same loss."""
+    from graph_detr4d_b200.graphed import HostFeatureBuffer
+    sc = H.scene(B=1, T=1, Q=80)
+    model = _build("C", 6, 2).cuda()
+    feats16 = [f.to(torch.float16) for f in sc["feats"]]
+    feats = [f.float().cuda() for f in feats16]                      # fp16-exact fp32 maps, resident
+    metas = sc["metas"]
+    gout = torch.randn(2, 80, 1, 256, generator=torch.Generator().manual_seed(5)).cuda()
+
+    def fl(fs):
+        st, _, refs = model(fs, metas, 1)
+        return (st * gout).mean()
+
+    stepper = GraphedTrainStep(model, fl, [f * 0.0 for f in feats], metas, warmup_iters=2, lr=0.0)
+    shapes = [tuple(f.shape) for f in feats]
+    host16, host32 = HostFeatureBuffer(shapes, torch.float16), HostFeatureBuffer(shapes, torch.float32)
+    for v16, v32, f in zip(host16.views, host32.views, feats16):
+        v16.copy_(f)
+        v32.copy_(f.float())
+    assert host16.nbytes * 2 == host32.nbytes
+    stepper.set_inputs(feats, metas)
+    l_res = float(stepper.step())
+    stepper.set_inputs([f * 0.0 for f in feats], metas)              # make sure the next result comes from the wire
+    stepper.prefetch(host16)
+    stepper.commit(metas)
+    l_16 = float(stepper.step())
+    assert all(torch.equal(a.detach(), b) for a, b in zip(stepper.static_feats, feats))
+    stepper.reset_pipeline()
+    stepper.set_inputs([f * 0.0 for f in feats], metas)
+    stepper.prefetch(host32)
+    stepper.commit(metas)
+    l_32 = float(stepper.step())
+    # lr = 0: the weights do not move, so the three steps see the same model; atomics-order noise only
+    assert abs(l_16 - l_res) <= 1e-5 * abs(l_res) and abs(l_32 - l_res) <= 1e-5 * abs(l_res) and l_res != 0.0

@@ -216,21 +216,22 @@ def test_mode_c_wide_forward_backward(C, dtype, T, Q):
         assert H.rel_err(fg.grad.cpu(), fo.grad) <= GRAD_TOL
 
 
-@pytest.mark.parametrize("dtype,T,B,static", [(torch.float32, 1, 1, False), (torch.float32, 2, 2, False),
-                                              (torch.bfloat16, 2, 1, False), (torch.float32, 1, 1, True)])
-def test_sorted_backward_equals_atomics_backward_and_leaves_its_scratch_clean(dtype, T, B, static):
+@pytest.mark.parametrize("dtype,T,B,static,C", [(torch.float32, 1, 1, False, 256), (torch.float32, 2, 2, False, 256),
+                                                (torch.bfloat16, 2, 1, False, 256), (torch.float32, 1, 1, True, 256),
+                                                (torch.bfloat16, 1, 1, False, 512), (torch.float32, 1, 1, False, 128)])
+def test_sorted_backward_equals_atomics_backward_and_leaves_its_scratch_clean(dtype, T, B, static, C):
     """The owner-computes backward (xview_bwd_sorted.cu: sort by pixel row, one reduction per run) against
     the atomics backward (xview_bwd.cu): same gradients up to fp32 summation order; calling it three
     times on one scratch gives the same answer (its counters and histogram are left zeroed); with the
     static one-warp-per-item schedule too; NULL feature-gradient maps are skipped."""
-    sc = H.scene(B=B, T=T, Q=333)
+    sc = H.scene(B=B, T=T, Q=333, C=C)
     logits, offsets, cam = H.rand_inputs_c(sc)
     packed = _pack(sc["feats"], dtype)
     cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=True)
     args = (cfg, packed.levels, B, sc["N"], sc["ref"].cuda(), logits.cuda(), offsets.cuda(), cam.cuda(),
             sc["l2i"].cuda())
     g = torch.Generator().manual_seed(3)
-    go = torch.randn(B, 8, 333, 256, generator=g).cuda()
+    go = torch.randn(B, 8, 333, C, generator=g).cuda()
     gw = torch.randn(B, 8, 333, generator=g).cuda()
     res = {}
     ops.DYNAMIC_SCHEDULE = not static
