@@ -20,6 +20,7 @@ F32, BF16 = 0, 1
 FLAG_TMA_FORWARD = 1
 FLAG_L2_PREFETCH = 2
 FLAG_BWD_SKIP_OWNER = 4        # measurement only (include/gd4d_xview.h)
+FLAG_BWD_PRESORTED = 8
 
 EXPORTS = (
     "gd4d_abi_version",
@@ -29,6 +30,7 @@ EXPORTS = (
     "gd4d_xview_forward",
     "gd4d_xview_backward",
     "gd4d_xview_bwd_ws_bytes",
+    "gd4d_xview_backward_sort",
     "gd4d_pack_nchw",
     "gd4d_unpack_nhwc",
     # include/gd4d_glue.h
@@ -135,6 +137,8 @@ def load(build_if_missing: bool = True):
         lib.gd4d_xview_forward.argtypes = [C.POINTER(XViewParams), C.c_void_p]
         lib.gd4d_xview_backward.restype = C.c_int
         lib.gd4d_xview_backward.argtypes = [C.POINTER(XViewParams), C.c_void_p]
+        lib.gd4d_xview_backward_sort.restype = C.c_int
+        lib.gd4d_xview_backward_sort.argtypes = [C.POINTER(XViewParams), C.c_void_p]
         lib.gd4d_xview_bwd_ws_bytes.restype = C.c_int64
         lib.gd4d_xview_bwd_ws_bytes.argtypes = [C.POINTER(XViewParams)]
         lib.gd4d_pack_nchw.restype = C.c_int

@@ -5,7 +5,7 @@
 namespace gd4d {
 int dispatch_forward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
 int dispatch_backward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
-int dispatch_backward_sorted(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
+int dispatch_backward_sorted(const gd4d_xview_params& p, const LaunchGeom& g, int stages, cudaStream_t stream);
 long long sorted_ws_bytes(const gd4d_xview_params& p);
 int dispatch_forward_tma(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream);
 int dispatch_v2(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream, bool backward);
@@ -132,8 +132,23 @@ int gd4d_xview_backward(const gd4d_xview_params* p, void* cuda_stream) {
   if (p->mode == GD4D_MODE_V2)
     return gd4d::dispatch_v2(*p, g, static_cast<cudaStream_t>(cuda_stream), true);
   if (p->mode == GD4D_MODE_C && p->wide && p->bwd_ws != nullptr)
-    return gd4d::dispatch_backward_sorted(*p, g, static_cast<cudaStream_t>(cuda_stream));
+    return gd4d::dispatch_backward_sorted(*p, g, (p->flags & GD4D_FLAG_BWD_PRESORTED) ? 2 : 3,
+                                          static_cast<cudaStream_t>(cuda_stream));
+  if (p->flags & GD4D_FLAG_BWD_PRESORTED) return GD4D_ERR_UNSUPPORTED;
   return gd4d::dispatch_backward(*p, g, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int gd4d_xview_backward_sort(const gd4d_xview_params* p, void* cuda_stream) {
+  gd4d::LaunchGeom g{};
+  gd4d_xview_params q;
+  if (p == nullptr) return GD4D_ERR_NULL;
+  q = *p;
+  static float dummy_aligned[4] __attribute__((aligned(16)));
+  if (q.grad_out == nullptr) q.grad_out = dummy_aligned;       // not read by the sort; validate() wants it non-NULL
+  const int st = gd4d::validate(&q, true, &g);
+  if (st != GD4D_OK) return st;
+  if (p->mode != GD4D_MODE_C || !p->wide || p->bwd_ws == nullptr) return GD4D_ERR_UNSUPPORTED;
+  return gd4d::dispatch_backward_sorted(*p, g, 1, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int64_t gd4d_xview_bwd_ws_bytes(const gd4d_xview_params* p) {

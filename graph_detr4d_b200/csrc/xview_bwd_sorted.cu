@@ -11,7 +11,8 @@
 // registers, and retires the row with ONE reduction.  Reductions drop 486 k -> ~110 k, value-row
 // gathers 486 k -> ~110 k.
 //
-// Five stream-ordered launches (all through gd4d_xview_backward when p.bwd_ws is set):
+// Five stream-ordered launches (all through gd4d_xview_backward when p.bwd_ws is set; the first three -- the sort --
+// need only the forward's inputs and can run early, on another stream, through gd4d_xview_backward_sort):
 //   K1 emit      warp per (b,q,head): candidates + records exactly as xview_bwd.cu builds them; every
 //                in-map corner takes a slot in its row's histogram (atomicAdd returns its rank) and
 //                writes {row, rank, grad_out row, wt * w_corner} at cid = base + item*4 + corner
@@ -53,6 +54,8 @@ static long long ws_layout(const gd4d_xview_params& p, SortedWs* ws, char* base_
     R += static_cast<long long>(p.B) * p.N * p.level_h[l] * p.level_w[l];
   }
   if (R > 0x7ffffff0LL) return -1;
+  for (int l = 0; l < p.L; ++l)   // grad-map element offsets travel as int32
+    if (static_cast<long long>(p.B) * p.N * p.level_h[l] * p.level_w[l] * p.C > 0x7ffffff0LL) return -1;
   const long long items = static_cast<long long>(p.B) * p.Q * p.Hh * p.N * p.P * p.L;
   const long long cap = items * 4;
   if (cap > 0x7ffffff0LL) return -1;
@@ -134,15 +137,13 @@ xview_bwd_items_kernel(const __grid_constant__ gd4d_xview_params p, const __grid
       if (!FINISH) {
         const float cw[4] = {r.wt * r.w00, r.wt * r.w01, r.wt * r.w10, r.wt * r.w11};
         const VT* vbase = static_cast<const VT*>(p.value[l]);
-        float* gbase = p.grad_value[l];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           int4 lo = make_int4(0, 0, 0, 0), hi = make_int4(0, 0, -1, 0);
           if (o[j] != z) {                                       // in-map corner
             const int row = static_cast<int>(ws.level_row0[l] + o[j] / p.C);
             const unsigned long long vp = reinterpret_cast<unsigned long long>(vbase + o[j]);
-            const unsigned long long gp = gbase != nullptr ? reinterpret_cast<unsigned long long>(gbase + o[j]) : 0ull;
-            lo = make_int4(static_cast<int>(vp), static_cast<int>(vp >> 32), static_cast<int>(gp), static_cast<int>(gp >> 32));
+            lo = make_int4(static_cast<int>(vp), static_cast<int>(vp >> 32), static_cast<int>(o[j]), l);
             hi = make_int4(go_row, __float_as_int(cw[j]), row, atomicAdd(ws.row_count + row, 1));
           }
           ws.rec[2 * (cid0 + j)] = lo;
@@ -292,7 +293,8 @@ __global__ void __launch_bounds__(256) xview_bwd_scan_kernel(const SortedWs ws) 
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) SRec {
   const void* vrow;   // value row of this contribution's pixel
-  float* gvrow;       // grad-map row (fp32), or NULL
+  int goff;           // element offset of the same row in the level's fp32 grad map (resolved by the owner: the
+  int level;          //   grad map need not exist yet when the sort runs)
   int go_row;         // grad_out row (b, head, q)
   float coef;         // wt * bilinear corner weight
   int cid;            // where its dot product goes
@@ -349,14 +351,13 @@ xview_bwd_owner_kernel(const __grid_constant__ gd4d_xview_params p, const __grid
     const int cnt = min(32, n - i0);
     // one record per lane
     SRec me;
-    me.vrow = nullptr; me.gvrow = nullptr; me.go_row = 0; me.coef = 0.f; me.cid = 0; me.row = -1;
+    me.vrow = nullptr; me.goff = 0; me.level = 0; me.go_row = 0; me.coef = 0.f; me.cid = 0; me.row = -1;
     if (lane < cnt) {
       const int4 lo = __ldg(reinterpret_cast<const int4*>(sorted + i0 + lane));
       const int4 hi = __ldg(reinterpret_cast<const int4*>(sorted + i0 + lane) + 1);
       me.vrow = reinterpret_cast<const void*>((static_cast<unsigned long long>(static_cast<unsigned>(lo.y)) << 32) |
                                               static_cast<unsigned>(lo.x));
-      me.gvrow = reinterpret_cast<float*>((static_cast<unsigned long long>(static_cast<unsigned>(lo.w)) << 32) |
-                                          static_cast<unsigned>(lo.z));
+      me.goff = lo.z; me.level = lo.w;
       me.go_row = hi.x; me.coef = __int_as_float(hi.y); me.cid = hi.z; me.row = hi.w;
     }
     const int prev = __shfl_up_sync(0xffffffffu, me.row, 1);
@@ -428,7 +429,11 @@ xview_bwd_owner_kernel(const __grid_constant__ gd4d_xview_params p, const __grid
         const int i = u0 + u;
         if ((starts >> i) & 1u) {                                       // warp-uniform: a new run
           flush();
-          cur_gv = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(me.gvrow), i);
+          {
+            float* gl = p.grad_value[__shfl_sync(0xffffffffu, me.level, i)];
+            const int goff = __shfl_sync(0xffffffffu, me.goff, i);
+            cur_gv = gl != nullptr ? reinterpret_cast<unsigned long long>(gl + goff) : 0ull;
+          }
           open = true;
           const unsigned char* slot = ring + (((u0 / U) & 1) * U + u) * kRowBytes;
 #pragma unroll
@@ -481,7 +486,8 @@ xview_bwd_owner_kernel(const __grid_constant__ gd4d_xview_params p, const __grid
 }
 
 template <typename VT>
-static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const SortedWs& ws, cudaStream_t stream) {
+static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const SortedWs& ws, int stages,
+                         cudaStream_t stream) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -500,9 +506,12 @@ static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const 
   // machine's warp slots empty.  One warp per (b, q, head), statically, all of them resident at once.
   gd4d_xview_params ps = p;
   ps.sched = nullptr;
-  emit<<<g.grid, block, smem, stream>>>(ps, ws, g.cand_cap);
-  xview_bwd_scan_kernel<<<ws.nblk, 256, 0, stream>>>(ws);
-  xview_bwd_scatter_kernel<<<sms * 16, 256, 0, stream>>>(ws);
+  if (stages & 1) {                                                  // the sort: needs the forward's inputs only
+    emit<<<g.grid, block, smem, stream>>>(ps, ws, g.cand_cap);
+    xview_bwd_scan_kernel<<<ws.nblk, 256, 0, stream>>>(ws);
+    xview_bwd_scatter_kernel<<<sms * 16, 256, 0, stream>>>(ws);
+  }
+  if (!(stages & 2)) return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
   if (!(p.flags & GD4D_FLAG_BWD_SKIP_OWNER)) {
     const int osmem = kOwnerWarps * kOwnerSlots * 512 * g.nv;          // per-warp value-row rings
     auto own1 = xview_bwd_owner_kernel<VT, 1>;
@@ -518,15 +527,17 @@ static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const 
   return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
 }
 
-int dispatch_backward_sorted(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream) {
+// stages: 1 = sort only (emit, scan, scatter: gd4d_xview_backward_sort), 2 = owner + finish on a scratch sorted
+// earlier (GD4D_FLAG_BWD_PRESORTED), 3 = the whole backward
+int dispatch_backward_sorted(const gd4d_xview_params& p, const LaunchGeom& g, int stages, cudaStream_t stream) {
   if (p.mode != GD4D_MODE_C || !p.wide || p.bwd_ws == nullptr) return GD4D_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(p.bwd_ws) & 255u) != 0) return GD4D_ERR_ALIGN;
   SortedWs ws;
   const long long need = ws_layout(p, &ws, static_cast<char*>(p.bwd_ws));
   if (need < 0) return GD4D_ERR_DIMS;
   if (p.bwd_ws_bytes < need) return GD4D_ERR_DIMS;
-  return p.value_dtype == GD4D_BF16 ? launch_sorted<__nv_bfloat16>(p, g, ws, stream)
-                                    : launch_sorted<float>(p, g, ws, stream);
+  return p.value_dtype == GD4D_BF16 ? launch_sorted<__nv_bfloat16>(p, g, ws, stages, stream)
+                                    : launch_sorted<float>(p, g, ws, stages, stream);
 }
 
 }  // namespace gd4d

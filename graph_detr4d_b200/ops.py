@@ -110,6 +110,54 @@ def _attach_bwd_ws(p: XViewParams, device) -> int:
     return 5
 
 
+# Sorted backward, opt-in (GD4D_PRESORT=1): run its sort stage (emit, scan, scatter -- forward inputs only) right after
+# the FORWARD kernel on a side stream, so the backward call is only the owner and finish kernels.  One scratch per
+# (forward, backward) pair, owned by the autograd node; under CUDA-graph capture the side stream forks from and joins
+# back into the capture through the events below (needs the node's backward inside the same capture).
+# Measured r2 (tools/ab_step.py, same process): 4.599 vs 4.579 ms at N = 6, 5.292 vs 5.303 ms at N = 12 -- no gain:
+# the 900-CTA emit kernel does not hide under the layer's GEMMs, it competes with them for the same SMs.  Off.
+PRESORT = os.environ.get("GD4D_PRESORT", "0") != "0"
+_SORT_STREAMS = {}
+
+
+def _presort(p: XViewParams, device):
+    """``p``: parameters filled as for the backward (forward inputs are enough).  -> (scratch, done-event) or None."""
+    if not (PRESORT and sorted_backward_active(p.mode, bool(p.wide), p.value_dtype)):
+        return None
+    lib = _lib.load()
+    need = int(lib.gd4d_xview_bwd_ws_bytes(C.byref(p)))
+    if need < 0:
+        return None
+    rows = sum(p.B * p.N * p.level_h[l] * p.level_w[l] for l in range(p.L))
+    with torch.no_grad():
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        ws[:256 + (4 * rows + 255) // 256 * 256].zero_()
+    p.bwd_ws, p.bwd_ws_bytes = ws.data_ptr(), ws.numel()
+    dev = torch.device(device)
+    side = _SORT_STREAMS.get(dev.index)
+    if side is None:
+        side = _SORT_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    side.wait_stream(main)                                  # inputs written, scratch head zeroed
+    st = lib.gd4d_xview_backward_sort(C.byref(p), side.cuda_stream)
+    _lib.check(st, "gd4d_xview_backward_sort")
+    _count(3)
+    done = torch.cuda.Event()
+    done.record(side)
+    if not torch.cuda.is_current_stream_capturing():
+        ws.record_stream(side)
+    return ws, done
+
+
+def _use_presorted(p: XViewParams, presort, device) -> int:
+    """Point ``p`` at a scratch sorted by ``_presort`` and make the current stream wait for it."""
+    ws, done = presort
+    torch.cuda.current_stream(device).wait_event(done)
+    p.bwd_ws, p.bwd_ws_bytes = ws.data_ptr(), ws.numel()
+    p.flags |= _lib.FLAG_BWD_PRESORTED
+    return 2
+
+
 def _require_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: the cross-view sampling path has no CPU "
@@ -414,7 +462,7 @@ def xview_forward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: i
 
 def xview_backward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
                    offsets, cam_logits, lidar2img, grad_out, grad_values: Optional[Sequence[torch.Tensor]],
-                   need_ref: bool = True, need_offsets: bool = True, grad_wsum=None):
+                   need_ref: bool = True, need_offsets: bool = True, grad_wsum=None, presort=None):
     """One fused backward launch.  ``grad_values`` (fp32 channel-last, same shapes as
     ``values``) are ACCUMULATED into; the small gradients are returned fresh."""
     grad_out = _f32c(grad_out, "grad_out")
@@ -445,7 +493,7 @@ def xview_backward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: 
     p.grad_offsets = g_off.data_ptr() if g_off is not None else None
     p.grad_cam_logits = g_cam.data_ptr() if g_cam is not None else None
     p.grad_ref = g_ref.data_ptr() if g_ref is not None else None
-    n_launch = _attach_bwd_ws(p, ref.device)
+    n_launch = _use_presorted(p, presort, ref.device) if presort is not None else _attach_bwd_ws(p, ref.device)
     st = _lib.load().gd4d_xview_backward(C.byref(p), _stream_ptr(ref.device))
     _lib.check(st, "gd4d_xview_backward")
     _count(n_launch)
@@ -552,7 +600,7 @@ def xview_forward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layout
 
 
 def xview_backward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layout: GenLayout, lidar2img,
-                       grad_out, grad_values, need_ref: bool = True, grad_wsum=None):
+                       grad_out, grad_values, need_ref: bool = True, grad_wsum=None, presort=None):
     """Backward of ``xview_forward_gen``: returns (grad_gen (B,Q,width), grad_ref|None), one
     zero-filled allocation for both."""
     grad_out = _f32c(grad_out, "grad_out")
@@ -575,7 +623,7 @@ def xview_backward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layou
     p.grad_offsets = base + 4 * layout.offsets
     p.grad_cam_logits = base + 4 * layout.cam
     p.grad_ref = g_ref.data_ptr() if g_ref is not None else None
-    n_launch = _attach_bwd_ws(p, ref.device)
+    n_launch = _use_presorted(p, presort, ref.device) if presort is not None else _attach_bwd_ws(p, ref.device)
     _lib.check(_lib.load().gd4d_xview_backward(C.byref(p), _stream_ptr(ref.device)), "gd4d_xview_backward")
     _count(n_launch)
     return g_gen, g_ref
@@ -609,6 +657,9 @@ class _XViewFn(torch.autograd.Function):
         empty = ref_c.new_empty(0)
         ctx.save_for_backward(ref_c, attn_c, off_c if off_c is not None else empty,
                               cam_c if cam_c is not None else empty, l2i_c, *values)
+        ctx.presort = None
+        if cfg.wide and cfg.mode == MODE_C and any(ctx.needs_input_grad):
+            ctx.presort = _presort(_fill_params(cfg, values, B, N, ref_c, attn_c, off_c, cam_c, l2i_c), ref_c.device)
         return res
 
     @staticmethod
@@ -627,7 +678,8 @@ class _XViewFn(torch.autograd.Function):
         g_attn, g_off, g_cam, g_ref = xview_backward(
             ctx.cfg, values, ctx.B, ctx.N, ref, attn, off, cam, l2i, grad_out, grad_values,
             need_ref=nd[_I_REF], need_offsets=ctx.has_off and nd[_I_OFF],
-            grad_wsum=grad_wsum if ctx.cfg.wide else None)
+            grad_wsum=grad_wsum if ctx.cfg.wide else None, presort=ctx.presort)
+        ctx.presort = None
         gv = [None] * len(values)
         if need_values and not use_sink:
             gv = [g if g.dtype == v.dtype else g.to(v.dtype) for g, v in zip(grad_values, values)]
@@ -648,6 +700,10 @@ class _XViewGenFn(torch.autograd.Function):
         res = xview_forward_gen(cfg, values, B, N, ref_c, gen_c, layout, l2i_c)
         ctx.cfg, ctx.B, ctx.N, ctx.sink, ctx.layout = cfg, B, N, sink, layout
         ctx.save_for_backward(ref_c, gen_c, l2i_c, *values)
+        ctx.presort = None
+        if cfg.wide and any(ctx.needs_input_grad):
+            ctx.presort = _presort(_fill_params(cfg, values, B, N, ref_c, None, None, None, l2i_c, gen=gen_c,
+                                                layout=layout), ref_c.device)
         return res
 
     @staticmethod
@@ -663,7 +719,8 @@ class _XViewGenFn(torch.autograd.Function):
             grad_values = [torch.zeros(v.shape, device=v.device, dtype=torch.float32) for v in values]
         g_gen, g_ref = xview_backward_gen(ctx.cfg, values, ctx.B, ctx.N, ref, gen, ctx.layout, l2i, grad_out,
                                           grad_values, need_ref=nd[3],
-                                          grad_wsum=grad_wsum if ctx.cfg.wide else None)
+                                          grad_wsum=grad_wsum if ctx.cfg.wide else None, presort=ctx.presort)
+        ctx.presort = None
         gv = [None] * len(values)
         if need_values and not use_sink:
             gv = [g if g.dtype == v.dtype else g.to(v.dtype) for g, v in zip(grad_values, values)]

@@ -71,6 +71,9 @@ typedef enum gd4d_dtype { GD4D_F32 = 0, GD4D_BF16 = 1 } gd4d_dtype;
  * run the sorted backward WITHOUT its owner pass -- the feature gradient is not produced and the small gradients
  * are meaningless */
 #define GD4D_FLAG_BWD_SKIP_OWNER 4u
+/* backward, sorted path: bwd_ws already holds this call's sorted contribution records (gd4d_xview_backward_sort ran
+ * on the same scratch with the same forward inputs): run only the owner and finish kernels */
+#define GD4D_FLAG_BWD_PRESORTED 8u
 
 /*
  * One decoder-layer invocation.  All pointers are device pointers.
@@ -179,6 +182,11 @@ GD4D_API int gd4d_xview_launch_info(const gd4d_xview_params* p, int32_t* grid, i
 
 GD4D_API int gd4d_xview_forward(const gd4d_xview_params* p, void* cuda_stream);
 GD4D_API int gd4d_xview_backward(const gd4d_xview_params* p, void* cuda_stream);
+/* The sort stage of the sorted backward alone (emit, scan, scatter into p->bwd_ws): needs only the FORWARD inputs
+ * (value maps, ref, logits, offsets, lidar2img), not grad_out nor the grad maps, so a caller can run it right after
+ * the forward on another stream and later call gd4d_xview_backward with GD4D_FLAG_BWD_PRESORTED on the same scratch.
+ * One scratch per in-flight (forward, backward) pair. */
+GD4D_API int gd4d_xview_backward_sort(const gd4d_xview_params* p, void* cuda_stream);
 /* bytes of bwd_ws the sorted backward needs for these dimensions (mode C, wide); negative status otherwise */
 GD4D_API int64_t gd4d_xview_bwd_ws_bytes(const gd4d_xview_params* p);
 

@@ -373,3 +373,29 @@ def test_pack_kernels_exact_all_paths(C, H_, W_):
     want = f.flatten(0, 1).permute(0, 2, 3, 1).contiguous()
     assert torch.equal(ops.pack_level(f), want)
     assert torch.equal(ops.pack_level(f, torch.bfloat16), want.to(torch.bfloat16))
+
+
+def test_presorted_backward_on_a_side_stream_matches():
+    """gd4d_xview_backward_sort right after the forward on a side stream + GD4D_FLAG_BWD_PRESORTED backward
+    (ops.PRESORT, opt-in) gives the gradients of the one-call sorted backward."""
+    sc = H.scene(B=1, T=2, Q=200)
+    logits, offsets, cam = H.rand_inputs_c(sc)
+    cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=True)
+    g = torch.Generator().manual_seed(4)
+    g1, g2 = torch.randn(1, 8, 200, 256, generator=g).cuda(), torch.randn(1, 8, 200, generator=g).cuda()
+    res = {}
+    try:
+        for pre in (False, True):
+            ops.PRESORT, ops.SORTED_BACKWARD = pre, True
+            feats = [_leaf(f.cuda()) for f in sc["feats"]]
+            ref, log, off, cm = (_leaf(t.cuda()) for t in (sc["ref"], logits, offsets, cam))
+            packed = ops.pack_features(feats)
+            n0 = ops.launch_count()
+            agg, ws = ops.xview_attention(cfg, packed, ref, log, off, cm, sc["l2i"].cuda())
+            assert ops.launch_count() - n0 == (4 if pre else 1)            # forward (+ the 3 sort kernels)
+            ((agg * g1).sum() + (ws * g2).sum()).backward()
+            res[pre] = [t.grad.clone() for t in (ref, log, off, cm, *feats)]
+    finally:
+        ops.PRESORT, ops.SORTED_BACKWARD = False, "auto"
+    for a, b in zip(res[True], res[False]):
+        assert H.rel_err(a, b) <= 1e-5 and float(b.abs().max()) > 0
