@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libgd4d_xview.so")
 SOURCES = ["c_abi.cu", "xview_fwd.cu", "xview_fwd_tma.cu", "xview_bwd.cu", "xview_bwd_sorted.cu", "xview_v2.cu", "pack.cu", "glue.cu", "gemm_tf32x3.cu", "sgemm_small.cu", "frustum_pe.cu", "match_cost.cu", "fpe.cu"]
-HEADERS = ["xview_common.cuh", "xview_records.cuh", "xview_bwd_records.cuh", os.path.join("..", "..", "include", "gd4d_xview.h"),
+HEADERS = ["xview_common.cuh", "xview_records.cuh", "xview_bwd_records.cuh", "xview_sorted_ws.cuh", os.path.join("..", "..", "include", "gd4d_xview.h"),
            os.path.join("..", "..", "include", "gd4d_glue.h"),
            os.path.join("..", "..", "include", "gd4d_frustum.h"),
            os.path.join("..", "..", "include", "gd4d_assign.h"),

@@ -21,6 +21,8 @@ FLAG_TMA_FORWARD = 1
 FLAG_L2_PREFETCH = 2
 FLAG_BWD_SKIP_OWNER = 4        # measurement only (include/gd4d_xview.h)
 FLAG_BWD_PRESORTED = 8
+FLAG_FWD_EMIT = 16
+FLAG_BWD_EMITTED = 32
 
 EXPORTS = (
     "gd4d_abi_version",

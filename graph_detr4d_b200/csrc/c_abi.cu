@@ -132,9 +132,10 @@ int gd4d_xview_backward(const gd4d_xview_params* p, void* cuda_stream) {
   if (p->mode == GD4D_MODE_V2)
     return gd4d::dispatch_v2(*p, g, static_cast<cudaStream_t>(cuda_stream), true);
   if (p->mode == GD4D_MODE_C && p->wide && p->bwd_ws != nullptr)
-    return gd4d::dispatch_backward_sorted(*p, g, (p->flags & GD4D_FLAG_BWD_PRESORTED) ? 2 : 3,
+    return gd4d::dispatch_backward_sorted(*p, g, (p->flags & GD4D_FLAG_BWD_PRESORTED) ? 4 :
+                                                 (p->flags & GD4D_FLAG_BWD_EMITTED) ? 6 : 7,
                                           static_cast<cudaStream_t>(cuda_stream));
-  if (p->flags & GD4D_FLAG_BWD_PRESORTED) return GD4D_ERR_UNSUPPORTED;
+  if (p->flags & (GD4D_FLAG_BWD_PRESORTED | GD4D_FLAG_BWD_EMITTED)) return GD4D_ERR_UNSUPPORTED;
   return gd4d::dispatch_backward(*p, g, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -148,7 +149,7 @@ int gd4d_xview_backward_sort(const gd4d_xview_params* p, void* cuda_stream) {
   const int st = gd4d::validate(&q, true, &g);
   if (st != GD4D_OK) return st;
   if (p->mode != GD4D_MODE_C || !p->wide || p->bwd_ws == nullptr) return GD4D_ERR_UNSUPPORTED;
-  return gd4d::dispatch_backward_sorted(*p, g, 1, static_cast<cudaStream_t>(cuda_stream));
+  return gd4d::dispatch_backward_sorted(*p, g, 3, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int64_t gd4d_xview_bwd_ws_bytes(const gd4d_xview_params* p) {

@@ -27,27 +27,13 @@
 // Results equal xview_bwd.cu up to fp32 summation order (tests/test_xview_gpu.py runs both).
 #include "xview_common.cuh"
 #include "xview_bwd_records.cuh"
+#include "xview_sorted_ws.cuh"
 
 namespace gd4d {
 
-struct SortedWs {
-  unsigned* counters;   // [0] slots handed out by K1 (4 per item), [1] number of sorted contributions,
-                        // [2] K2 blocks done
-  int* row_count;       // R    histogram; zero on entry, re-zeroed by K4
-  int* row_start;       // R    block-local exclusive prefix
-  int* block_sums;      // nblk exclusive prefix of the 2048-row block totals
-  int* base;            // B*Q*Hh  first cid of each (b,q,head)
-  int4* rec;            // cap  32-byte records (two int4): {value row ptr, grad-map row ptr | go_row, coef, row | -1, rank}
-  int4* sorted;         // cap  32-byte SRec records (two int4 each), ordered by pixel row
-  float* dots;          // cap  value_row . grad_out_row per contribution
-  long long level_row0[GD4D_MAX_LEVELS + 1];   // first global row of each level (+ total)
-  int R, nblk;
-  long long cap;
-};
-
 constexpr int kScanBlock = 2048;   // rows per K2 block (256 threads x 8)
 
-static long long ws_layout(const gd4d_xview_params& p, SortedWs* ws, char* base_ptr) {
+long long sorted_ws_layout(const gd4d_xview_params& p, SortedWs* ws, char* base_ptr) {
   long long R = 0;
   for (int l = 0; l < p.L; ++l) {
     if (ws) ws->level_row0[l] = R;
@@ -80,7 +66,7 @@ static long long ws_layout(const gd4d_xview_params& p, SortedWs* ws, char* base_
   return off;
 }
 
-long long sorted_ws_bytes(const gd4d_xview_params& p) { return ws_layout(p, nullptr, nullptr); }
+long long sorted_ws_bytes(const gd4d_xview_params& p) { return sorted_ws_layout(p, nullptr, nullptr); }
 
 // ------------------------------------------------------------------------------------------------
 // K1 emit / K5 finish: one kernel body, warp per (b, q, head), one LANE per (candidate, level) item
@@ -139,15 +125,9 @@ xview_bwd_items_kernel(const __grid_constant__ gd4d_xview_params p, const __grid
         const VT* vbase = static_cast<const VT*>(p.value[l]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          int4 lo = make_int4(0, 0, 0, 0), hi = make_int4(0, 0, -1, 0);
-          if (o[j] != z) {                                       // in-map corner
-            const int row = static_cast<int>(ws.level_row0[l] + o[j] / p.C);
-            const unsigned long long vp = reinterpret_cast<unsigned long long>(vbase + o[j]);
-            lo = make_int4(static_cast<int>(vp), static_cast<int>(vp >> 32), static_cast<int>(o[j]), l);
-            hi = make_int4(go_row, __float_as_int(cw[j]), row, atomicAdd(ws.row_count + row, 1));
-          }
-          ws.rec[2 * (cid0 + j)] = lo;
-          ws.rec[2 * (cid0 + j) + 1] = hi;
+          const bool in_map = o[j] != z;
+          emit_contribution(ws, cid0 + j, in_map, vbase + o[j], o[j], l,
+                            in_map ? static_cast<int>(ws.level_row0[l] + o[j] / p.C) : -1, go_row, cw[j]);
         }
       } else {
         float d[4];
@@ -506,12 +486,12 @@ static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const 
   // machine's warp slots empty.  One warp per (b, q, head), statically, all of them resident at once.
   gd4d_xview_params ps = p;
   ps.sched = nullptr;
-  if (stages & 1) {                                                  // the sort: needs the forward's inputs only
-    emit<<<g.grid, block, smem, stream>>>(ps, ws, g.cand_cap);
+  if (stages & 1) emit<<<g.grid, block, smem, stream>>>(ps, ws, g.cand_cap);   // needs the forward's inputs only
+  if (stages & 2) {
     xview_bwd_scan_kernel<<<ws.nblk, 256, 0, stream>>>(ws);
     xview_bwd_scatter_kernel<<<sms * 16, 256, 0, stream>>>(ws);
   }
-  if (!(stages & 2)) return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
+  if (!(stages & 4)) return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
   if (!(p.flags & GD4D_FLAG_BWD_SKIP_OWNER)) {
     const int osmem = kOwnerWarps * kOwnerSlots * 512 * g.nv;          // per-warp value-row rings
     auto own1 = xview_bwd_owner_kernel<VT, 1>;
@@ -527,13 +507,14 @@ static int launch_sorted(const gd4d_xview_params& p, const LaunchGeom& g, const 
   return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
 }
 
-// stages: 1 = sort only (emit, scan, scatter: gd4d_xview_backward_sort), 2 = owner + finish on a scratch sorted
-// earlier (GD4D_FLAG_BWD_PRESORTED), 3 = the whole backward
+// stages (bits): 1 = emit, 2 = scan + scatter, 4 = owner + finish.  7 = the whole backward; 3 = the sort alone
+// (gd4d_xview_backward_sort); 4 = on a scratch sorted earlier (GD4D_FLAG_BWD_PRESORTED); 6 = on records the
+// FORWARD kernel emitted (GD4D_FLAG_FWD_EMIT on the forward call, GD4D_FLAG_BWD_EMITTED here)
 int dispatch_backward_sorted(const gd4d_xview_params& p, const LaunchGeom& g, int stages, cudaStream_t stream) {
   if (p.mode != GD4D_MODE_C || !p.wide || p.bwd_ws == nullptr) return GD4D_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(p.bwd_ws) & 255u) != 0) return GD4D_ERR_ALIGN;
   SortedWs ws;
-  const long long need = ws_layout(p, &ws, static_cast<char*>(p.bwd_ws));
+  const long long need = sorted_ws_layout(p, &ws, static_cast<char*>(p.bwd_ws));
   if (need < 0) return GD4D_ERR_DIMS;
   if (p.bwd_ws_bytes < need) return GD4D_ERR_DIMS;
   return p.value_dtype == GD4D_BF16 ? launch_sorted<__nv_bfloat16>(p, g, ws, stages, stream)

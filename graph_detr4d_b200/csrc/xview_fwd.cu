@@ -27,12 +27,16 @@
 //   mode C  deform3d_cross_attn.py:227-258, 274, 281-284, 301-304, 320-324
 #include "xview_common.cuh"
 #include "xview_records.cuh"
+#include "xview_sorted_ws.cuh"
 
 namespace gd4d {
 
-template <int MODE, typename VT, int LANES, int NV>
+// EMIT (mode C wide only, GD4D_FLAG_FWD_EMIT): the lane that builds an item's gather record also writes the item's
+// four corner contributions for the sorted backward (xview_bwd_sorted.cu) -- it holds exactly what that backward's
+// emit kernel would recompute (corner rows, wt * bilinear weights) -- and takes their ranks in the row histogram.
+template <int MODE, typename VT, int LANES, int NV, bool EMIT = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (LANES == 32) ? 2 : 3)
-xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap) {
+xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap, const __grid_constant__ SortedWs ews) {
   constexpr int VEC = Slice<VT>::VEC;
   constexpr int PL = VEC * NV;
   constexpr int GROUPS = 32 / LANES;  // items per warp-wide load
@@ -63,9 +67,33 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
     for (int i = 0; i < PL; ++i) acc[i] = 0.f;
     float wsum_lane = 0.f;
     const int total = nvalid * p.L;
+    int emit_base = 0;
+    if (EMIT) {
+      unsigned v = 0;
+      if (lane == 0 && total > 0) v = atomicAdd(ews.counters, static_cast<unsigned>(4 * total));
+      emit_base = static_cast<int>(__shfl_sync(0xffffffffu, v, 0));
+      if (lane == 0) ews.base[w.bq * p.Hh + w.h] = emit_base;
+    }
     for (int c0 = 0; c0 < total; c0 += 32) {
       float wt_item;
-      recs[lane] = build_record<MODE, VT, WIDE>(p, cands, sw, c0 + lane, total, w, wsum_lane, wt_item);
+      const RecF rec = build_record<MODE, VT, WIDE>(p, cands, sw, c0 + lane, total, w, wsum_lane, wt_item);
+      recs[lane] = rec;
+      if (EMIT && c0 + lane < total) {
+        const int l = (c0 + lane) % p.L;
+        const char* vbase = static_cast<const char*>(p.value[l]);
+        const char* zrow = reinterpret_cast<const char*>(g_zero_row);
+        const long long rowb = static_cast<long long>(p.C) * sizeof(VT);
+        const int go_row = (w.b * p.Hh + w.h) * p.Q + w.q;
+        const char* ptr[4] = {rec.p00, rec.p01, rec.p10, rec.p11};
+        const float cw[4] = {rec.w00, rec.w01, rec.w10, rec.w11};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool in_map = ptr[j] != zrow;
+          const long long rl = in_map ? (ptr[j] - vbase) / rowb : 0;       // pixel row inside the level
+          emit_contribution(ews, emit_base + (c0 + lane) * 4 + j, in_map, ptr[j], rl * p.C, l,
+                            static_cast<int>(ews.level_row0[l] + rl), go_row, cw[j]);
+        }
+      }
       if (MODE != GD4D_MODE_C) sw[lane] = wt_item;   // mode A: applied AFTER nan_to_num(sample); sw is free (no softmax)
       __syncwarp();
       const int nchunk = min(32, total - c0);
@@ -163,9 +191,15 @@ xview_fwd_kernel(const __grid_constant__ gd4d_xview_params p, const int cand_cap
   work_end(p, wi);
 }
 
-template <int MODE, typename VT, int LANES, int NV>
+template <int MODE, typename VT, int LANES, int NV, bool EMIT = false>
 static int launch_fwd(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream_t stream) {
-  auto kern = xview_fwd_kernel<MODE, VT, LANES, NV>;
+  auto kern = xview_fwd_kernel<MODE, VT, LANES, NV, EMIT>;
+  SortedWs ews{};
+  if (EMIT) {
+    if ((reinterpret_cast<uintptr_t>(p.bwd_ws) & 255u) != 0) return GD4D_ERR_ALIGN;
+    const long long need = sorted_ws_layout(p, &ews, static_cast<char*>(p.bwd_ws));
+    if (need < 0 || p.bwd_ws_bytes < need) return GD4D_ERR_DIMS;
+  }
   if (g.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem);
     if (e != cudaSuccess) return GD4D_ERR_CUDA;
@@ -180,7 +214,7 @@ static int launch_fwd(const gd4d_xview_params& p, const LaunchGeom& g, cudaStrea
     const long long resident = static_cast<long long>(sms) * (occ > 0 ? occ : 1);
     if (resident < grid) grid = static_cast<int>(resident);
   }
-  kern<<<grid, g.block, g.smem, stream>>>(p, g.cand_cap);
+  kern<<<grid, g.block, g.smem, stream>>>(p, g.cand_cap, ews);
   return cudaGetLastError() == cudaSuccess ? GD4D_OK : GD4D_ERR_CUDA;
 }
 
@@ -195,6 +229,12 @@ int dispatch_forward(const gd4d_xview_params& p, const LaunchGeom& g, cudaStream
                 : launch_fwd<GD4D_MODE_C, float, 8, 1>(p, g, stream);
   }
   if (p.mode == GD4D_MODE_C && p.wide) {
+    if ((p.flags & GD4D_FLAG_FWD_EMIT) && p.bwd_ws != nullptr) {
+      if (bf16) return g.nv == 1 ? launch_fwd<GD4D_MODE_C, __nv_bfloat16, 32, 1, true>(p, g, stream)
+                                 : launch_fwd<GD4D_MODE_C, __nv_bfloat16, 32, 2, true>(p, g, stream);
+      return g.nv == 1 ? launch_fwd<GD4D_MODE_C, float, 32, 1, true>(p, g, stream)
+                       : launch_fwd<GD4D_MODE_C, float, 32, 2, true>(p, g, stream);
+    }
     if (bf16) return g.nv == 1 ? launch_fwd<GD4D_MODE_C, __nv_bfloat16, 32, 1>(p, g, stream)
                                : launch_fwd<GD4D_MODE_C, __nv_bfloat16, 32, 2>(p, g, stream);
     return g.nv == 1 ? launch_fwd<GD4D_MODE_C, float, 32, 1>(p, g, stream)

@@ -117,6 +117,10 @@ def _attach_bwd_ws(p: XViewParams, device) -> int:
 # Measured r2 (tools/ab_step.py, same process): 4.599 vs 4.579 ms at N = 6, 5.292 vs 5.303 ms at N = 12 -- no gain:
 # the 900-CTA emit kernel does not hide under the layer's GEMMs, it competes with them for the same SMs.  Off.
 PRESORT = os.environ.get("GD4D_PRESORT", "0") != "0"
+# Sorted backward: let the FORWARD kernel emit the contribution records (GD4D_FLAG_FWD_EMIT: it builds the same
+# per-item records anyway), so the backward call starts at the scan.  Scratch per (forward, backward) pair, owned by
+# the autograd node, same stream throughout.  GD4D_FWD_EMIT=0 keeps the emit kernel in the backward.
+FWD_EMIT = os.environ.get("GD4D_FWD_EMIT", "1") != "0"
 _SORT_STREAMS = {}
 
 
@@ -149,11 +153,32 @@ def _presort(p: XViewParams, device):
     return ws, done
 
 
-def _use_presorted(p: XViewParams, presort, device) -> int:
-    """Point ``p`` at a scratch sorted by ``_presort`` and make the current stream wait for it."""
-    ws, done = presort
-    torch.cuda.current_stream(device).wait_event(done)
+def _emit_scratch(p: XViewParams, device, needs_grad: bool):
+    """Scratch for a forward that emits the sorted backward's records: attaches it to ``p`` (forward params) and
+    returns the ``presort`` tuple the backward takes, or None when that path does not apply."""
+    if not (FWD_EMIT and not PRESORT and needs_grad and sorted_backward_active(p.mode, bool(p.wide), p.value_dtype)):
+        return None
+    need = int(_lib.load().gd4d_xview_bwd_ws_bytes(C.byref(p)))
+    if need < 0:
+        return None
+    rows = sum(p.B * p.N * p.level_h[l] * p.level_w[l] for l in range(p.L))
+    with torch.no_grad():
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        ws[:256 + (4 * rows + 255) // 256 * 256].zero_()
     p.bwd_ws, p.bwd_ws_bytes = ws.data_ptr(), ws.numel()
+    p.flags |= _lib.FLAG_FWD_EMIT
+    return ws, None
+
+
+def _use_presorted(p: XViewParams, presort, device) -> int:
+    """Point ``p`` at a scratch prepared earlier: sorted by ``_presort`` on the side stream (wait for it), or holding
+    the records the forward kernel emitted (same stream).  Returns the number of launches of the backward call."""
+    ws, done = presort
+    p.bwd_ws, p.bwd_ws_bytes = ws.data_ptr(), ws.numel()
+    if done is None:
+        p.flags |= _lib.FLAG_BWD_EMITTED
+        return 4
+    torch.cuda.current_stream(device).wait_event(done)
     p.flags |= _lib.FLAG_BWD_PRESORTED
     return 2
 
@@ -429,7 +454,7 @@ def _out_shape(cfg, B, Q, Cc):
 
 
 def xview_forward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: int, ref, attn_logits,
-                  offsets=None, cam_logits=None, lidar2img=None, want_mask: bool = False):
+                  offsets=None, cam_logits=None, lidar2img=None, want_mask: bool = False, emit_for_backward: bool = False):
     """One fused forward launch.
     narrow: returns (out (B,Q,C), mask|None);  wide: returns ((out (B,Hh,Q,C), wsum (B,Hh,Q)), mask|None)."""
     for v in values:
@@ -454,9 +479,12 @@ def xview_forward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: i
         shape = (B, Q, N) if cfg.mode != MODE_C else (B, N, Q, cfg.num_heads, cfg.num_points)
         mask = torch.zeros(shape, device=ref.device, dtype=torch.uint8)
         p.mask = mask.data_ptr()
+    emitted = _emit_scratch(p, ref.device, emit_for_backward)
     st = _lib.load().gd4d_xview_forward(C.byref(p), _stream_ptr(ref.device))
     _lib.check(st, "gd4d_xview_forward")
     _count()
+    if emit_for_backward:
+        return ((out, wsum) if cfg.wide else out), mask, emitted
     return ((out, wsum) if cfg.wide else out), mask
 
 
@@ -579,7 +607,8 @@ def _check_gen(cfg, B, N, L, ref, gen, layout: GenLayout, lidar2img):
         raise ValueError("generator blocks exceed the packed width")
 
 
-def xview_forward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layout: GenLayout, lidar2img):
+def xview_forward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layout: GenLayout, lidar2img,
+                      emit_for_backward: bool = False):
     """Mode C forward reading logits / offsets / camera logits as column blocks of ``gen``."""
     for v in values:
         _require_cuda(v, "value")
@@ -594,8 +623,11 @@ def xview_forward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layout
     if cfg.wide:
         wsum = torch.empty((B, cfg.num_heads, Q), device=ref.device, dtype=torch.float32)
         p.wsum = wsum.data_ptr()
+    emitted = _emit_scratch(p, ref.device, emit_for_backward)
     _lib.check(_lib.load().gd4d_xview_forward(C.byref(p), _stream_ptr(ref.device)), "gd4d_xview_forward")
     _count()
+    if emit_for_backward:
+        return ((out, wsum) if cfg.wide else out), emitted
     return (out, wsum) if cfg.wide else out
 
 
@@ -651,14 +683,16 @@ class _XViewFn(torch.autograd.Function):
         off_c = _f32c(offsets, "offsets")
         cam_c = _f32c(cam_logits, "cam_logits")
         l2i_c = _f32c(lidar2img, "lidar2img")
-        res, _ = xview_forward(cfg, values, B, N, ref_c, attn_c, off_c, cam_c, l2i_c)
+        want = bool(cfg.wide and cfg.mode == MODE_C and any(ctx.needs_input_grad))
+        r = xview_forward(cfg, values, B, N, ref_c, attn_c, off_c, cam_c, l2i_c, emit_for_backward=want)
+        res, emitted = (r[0], r[2]) if want else (r[0], None)
         ctx.cfg, ctx.B, ctx.N, ctx.sink = cfg, B, N, sink
         ctx.has_off, ctx.has_cam = offsets is not None, cam_logits is not None
         empty = ref_c.new_empty(0)
         ctx.save_for_backward(ref_c, attn_c, off_c if off_c is not None else empty,
                               cam_c if cam_c is not None else empty, l2i_c, *values)
-        ctx.presort = None
-        if cfg.wide and cfg.mode == MODE_C and any(ctx.needs_input_grad):
+        ctx.presort = emitted
+        if emitted is None and cfg.wide and cfg.mode == MODE_C and any(ctx.needs_input_grad):
             ctx.presort = _presort(_fill_params(cfg, values, B, N, ref_c, attn_c, off_c, cam_c, l2i_c), ref_c.device)
         return res
 
@@ -697,11 +731,13 @@ class _XViewGenFn(torch.autograd.Function):
     def forward(ctx, cfg: XViewConfig, B: int, N: int, ref, gen, layout: GenLayout, lidar2img,
                 token, sink, *values):
         ref_c, gen_c, l2i_c = _f32c(ref, "reference_points"), _f32c(gen, "gen"), _f32c(lidar2img, "lidar2img")
-        res = xview_forward_gen(cfg, values, B, N, ref_c, gen_c, layout, l2i_c)
+        want = bool(cfg.wide and any(ctx.needs_input_grad))
+        r = xview_forward_gen(cfg, values, B, N, ref_c, gen_c, layout, l2i_c, emit_for_backward=want)
+        res, emitted = r if want else (r, None)
         ctx.cfg, ctx.B, ctx.N, ctx.sink, ctx.layout = cfg, B, N, sink, layout
         ctx.save_for_backward(ref_c, gen_c, l2i_c, *values)
-        ctx.presort = None
-        if cfg.wide and any(ctx.needs_input_grad):
+        ctx.presort = emitted
+        if emitted is None and cfg.wide and any(ctx.needs_input_grad):
             ctx.presort = _presort(_fill_params(cfg, values, B, N, ref_c, None, None, None, l2i_c, gen=gen_c,
                                                 layout=layout), ref_c.device)
         return res

@@ -74,6 +74,11 @@ typedef enum gd4d_dtype { GD4D_F32 = 0, GD4D_BF16 = 1 } gd4d_dtype;
 /* backward, sorted path: bwd_ws already holds this call's sorted contribution records (gd4d_xview_backward_sort ran
  * on the same scratch with the same forward inputs): run only the owner and finish kernels */
 #define GD4D_FLAG_BWD_PRESORTED 8u
+/* forward, mode C wide, bwd_ws set: the forward kernel also EMITS the sorted backward's contribution records into
+ * bwd_ws (it builds the same per-item records anyway); the matching backward call passes GD4D_FLAG_BWD_EMITTED and
+ * the same scratch and skips its emit kernel.  One scratch per in-flight (forward, backward) pair. */
+#define GD4D_FLAG_FWD_EMIT 16u
+#define GD4D_FLAG_BWD_EMITTED 32u
 
 /*
  * One decoder-layer invocation.  All pointers are device pointers.

@@ -399,3 +399,35 @@ def test_presorted_backward_on_a_side_stream_matches():
         ops.PRESORT, ops.SORTED_BACKWARD = False, "auto"
     for a, b in zip(res[True], res[False]):
         assert H.rel_err(a, b) <= 1e-5 and float(b.abs().max()) > 0
+
+
+@pytest.mark.parametrize("dtype,T", [(torch.float32, 1), (torch.float32, 2), (torch.bfloat16, 2)])
+def test_forward_emitted_records_give_the_same_backward(dtype, T):
+    """GD4D_FLAG_FWD_EMIT: the forward kernel writes the sorted backward's contribution records itself; the backward
+    (scan, scatter, owner, finish: 4 launches) must equal the five-launch sorted backward and the oracle-checked
+    atomics backward; the forward outputs are untouched by the emission."""
+    sc = H.scene(B=1, T=T, Q=200)
+    logits, offsets, cam = H.rand_inputs_c(sc)
+    cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=True)
+    g = torch.Generator().manual_seed(4)
+    g1, g2 = torch.randn(1, 8, 200, 256, generator=g).cuda(), torch.randn(1, 8, 200, generator=g).cuda()
+    res = {}
+    try:
+        for name, srt, emit in (("atomics", False, False), ("sorted", True, False), ("emitted", True, True)):
+            ops.SORTED_BACKWARD, ops.FWD_EMIT, ops.PRESORT = srt, emit, False
+            feats = [_leaf(f.cuda()) for f in sc["feats"]]
+            ref, log, off, cm = (_leaf(t.cuda()) for t in (sc["ref"], logits, offsets, cam))
+            packed = ops.pack_features(feats, dtype)
+            agg, ws = ops.xview_attention(cfg, packed, ref, log, off, cm, sc["l2i"].cuda())
+            n0 = ops.launch_count()
+            ((agg * g1).sum() + (ws * g2).sum()).backward()
+            n_bwd = ops.launch_count() - n0
+            res[name] = ([agg.detach().clone(), ws.detach().clone()], [t.grad.clone() for t in (ref, log, off, cm, *feats)], n_bwd)
+    finally:
+        ops.SORTED_BACKWARD, ops.FWD_EMIT, ops.PRESORT = "auto", True, False
+    assert res["emitted"][2] < res["sorted"][2]                              # one kernel fewer in the backward
+    for a, b in zip(res["emitted"][0], res["atomics"][0]):
+        assert torch.equal(a, b)                                             # same forward, bit for bit
+    for key in ("sorted", "emitted"):
+        for a, b in zip(res[key][1], res["atomics"][1]):
+            assert H.rel_err(a, b) <= 2e-5 and float(b.abs().max()) > 0

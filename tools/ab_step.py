@@ -24,11 +24,13 @@ def build(name):
     fused.SOFTMAX_BWD = name != "no_smbwd"
     ops.SORTED_BACKWARD = {"sorted": True, "atomics": False}.get(name, "auto")
     ops.PRESORT = name == "presort"
+    ops.FWD_EMIT = name != "no_fwd_emit"
     model = copy.deepcopy(base_model)
     st = GraphedTrainStep(model, lambda f: bench.loss_fn(*(lambda s, _, r: (s, r))(*model(f, metas, 1))), feats, metas)
     fused.ENABLED, modules._PACKED_GEN, graphed.MULTI_TENSOR_ADAMW, fused.SOFTMAX_BWD = True, True, True, True
     ops.SORTED_BACKWARD = "auto"
     ops.PRESORT = False
+    ops.FWD_EMIT = True
     return st
 
 
