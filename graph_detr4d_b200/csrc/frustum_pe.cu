@@ -191,7 +191,7 @@ extern "C" int gd4d_frustum_pe_levels(const float* img2lidar, const uint8_t* con
     memcpy(&bits, &a.span[i], 4);
     if ((bits & 0x7fffffu) == 0x7fffffu) return GD4D_ERR_DIMS;   // Markstein's correction needs a non-all-ones significand
     a.rspan[i] = static_cast<float>(1.0 / static_cast<double>(a.span[i]));
-    if (!(fabsf(a.lo[i]) >= 1e-20f && fabsf(a.lo[i]) < 1e15f)) a.lo_is_normal = 0;
+    if (!(fabsf(a.lo[i]) >= 1e-20f && fabsf(a.lo[i]) < 1e15f && a.span[i] < 1e15f)) a.lo_is_normal = 0;
   }
   long long blocks = 0;
   for (int l = 0; l < num_levels; ++l) {

@@ -87,5 +87,33 @@ def test_launch_info_and_status_codes():
     pc = (C.c_float * 6)(*[0.0] * 6)
     assert lib.gd4d_frustum_pe(a, None, None, None, 6, 4, 4, 8, 928.0, 1600.0, 1.0, 0.1, pc, None) == -1
     assert lib.gd4d_frustum_pe(a, None, a, None, 6, 4, 4, 0, 928.0, 1600.0, 1.0, 0.1, pc, None) == -2
+    # r2 entry points: validation only, nothing launches without a GPU
+    ptrs = (C.c_void_p * 1)(a)
+    hs, ws_ = (C.c_int32 * 1)(4), (C.c_int32 * 1)(4)
+    assert lib.gd4d_frustum_pe_levels(a, None, ptrs, None, 6, 9, hs, ws_, 8, 928.0, 1600.0, 1.0, 0.1, pc, None) == -2   # > 8 levels
+    assert lib.gd4d_frustum_pe_levels(a, None, None, None, 6, 1, hs, ws_, 8, 928.0, 1600.0, 1.0, 0.1, pc, None) == -1
+    assert lib.gd4d_level_mask(None, a, 6, 4, 4, 928, 1600, None) == -1
+    assert lib.gd4d_sine_pe3d(a, a, a, 1, 6, 4, 4, 928, 1600, 7, 1, 6.28, 1e-6, -0.5, None) == -2          # odd num_feats
+    assert lib.gd4d_fpe_combine_fwd(a, a, a, a, a, 0, None) == -2
+    assert lib.gd4d_softmax_bwd(a, a, a, 10, 902, None) == -2                                          # cols % 4
+    assert lib.gd4d_softmax_bwd(a, a, a, 10, 2048, None) == -2                                         # cols > 1024
+    for fn in (lib.gd4d_gemm_tf32x3, lib.gd4d_sgemm_small):
+        assert fn(None, 256, 0, a, 256, 0, a, 256, None, 0, 900, 256, 256, 1, 0, 0, 0, None) == -1
+        assert fn(a, 256, 0, a, 256, 0, a, 256, None, 0, 900, 256, 0, 1, 0, 0, 0, None) == -2              # K = 0
+        assert fn(a + 4, 256, 0, a, 256, 0, a, 256, None, 0, 900, 256, 256, 1, 0, 0, 0, None) == -4        # alignment
+        assert fn(a, 254, 0, a, 256, 0, a, 256, None, 0, 900, 256, 256, 1, 0, 0, 0, None) == -4            # lda % 4
+        assert fn(a, 256, 0, a, 256, 0, a, 256, None, 0, 900, 256, 250, 1, 0, 0, 0, None) == -5            # K % 4
+    q = _valid_params()
+    assert lib.gd4d_xview_bwd_ws_bytes(C.byref(q)) == -5                                               # not wide mode C
+    q = _valid_params(); q.mode, q.wide = _lib.MODE_C, 1
+    need = lib.gd4d_xview_bwd_ws_bytes(C.byref(q))
+    assert need > 0 and need % 256 == 0
+    q.bwd_ws, q.bwd_ws_bytes = 0x10000, need - 256
+    assert lib.gd4d_xview_backward_sort(C.byref(q), None) == -2                                        # scratch too small
+    q.bwd_ws = 0x10010
+    assert lib.gd4d_xview_backward_sort(C.byref(q), None) == -4                                        # 256-byte alignment
+    q.bwd_ws, q.flags = None, _lib.FLAG_BWD_PRESORTED
+    q.grad_out = a
+    assert lib.gd4d_xview_backward(C.byref(q), None) == -5                                             # presorted without a scratch
     for code in (0, -1, -2, -3, -4, -5, -6, -99):
         assert len(_lib.strerror(code)) > 0
