@@ -526,7 +526,7 @@ def kernel_roofline(model, feats_dev, metas, T, dtype, dev, reps=300):
             return s.elapsed_time(e) / reps * 1e-3
 
         fwd_prep = [ops.prepare_forward(cfg, s, 1, N, ref, log, off, cam, l2i) for s in sets]
-        sorted_bwd = ops.sorted_backward_active(MODE_C, wide, ops._dtype_code(sets[0][0]))
+        sorted_bwd = ops.sorted_backward_active(MODE_C, wide, ops._dtype_code(sets[0][0]), N)
         bwd_prep = [ops.prepare_backward(cfg, s, 1, N, ref, log, off, cam, l2i, gout, g, grad_wsum=gws)
                     for s, g in zip(sets, gsets)]
         t_f = time_loop(lambda i: fwd_prep[i].launch())

@@ -35,6 +35,7 @@ EXPORTS = (
     "gd4d_xview_backward_sort",
     "gd4d_pack_nchw",
     "gd4d_unpack_nhwc",
+    "gd4d_unpack_nhwc_cast",
     # include/gd4d_glue.h
     "gd4d_inverse_sigmoid_fwd",
     "gd4d_inverse_sigmoid_bwd",
@@ -146,6 +147,9 @@ def load(build_if_missing: bool = True):
         lib.gd4d_pack_nchw.restype = C.c_int
         lib.gd4d_pack_nchw.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        lib.gd4d_unpack_nhwc_cast.restype = C.c_int
+        lib.gd4d_unpack_nhwc_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_void_p]
         lib.gd4d_unpack_nhwc.restype = C.c_int
         lib.gd4d_unpack_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_void_p]

@@ -180,4 +180,12 @@ int gd4d_unpack_nhwc(const float* src, float* dst, int64_t images, int32_t C, in
                              static_cast<cudaStream_t>(cuda_stream));
 }
 
+int gd4d_unpack_nhwc_cast(const float* src, void* dst, int32_t dst_dtype, int64_t images, int32_t C, int32_t H,
+                          int32_t W, void* cuda_stream) {
+  if (src == nullptr || dst == nullptr) return GD4D_ERR_NULL;
+  if (images <= 0 || C <= 0 || H <= 0 || W <= 0) return GD4D_ERR_DIMS;
+  if (dst_dtype != GD4D_F32 && dst_dtype != GD4D_BF16) return GD4D_ERR_UNSUPPORTED;
+  return gd4d::dispatch_pack(src, dst, GD4D_F32, dst_dtype, images, H * W, C, 1, static_cast<cudaStream_t>(cuda_stream));
+}
+
 }  // extern "C"

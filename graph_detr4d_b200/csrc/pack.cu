@@ -63,13 +63,25 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v
   *reinterpret_cast<uint2*>(p) = u;
 }
 
-template <typename TO>
-__global__ void __launch_bounds__(256) pack_nchw_v4_kernel(const float* __restrict__ src, TO* __restrict__ dst,
+// four consecutive source elements as float4 (fp32: one 16-byte load, bf16: one 8-byte load)
+template <typename TI>
+__device__ __forceinline__ float4 load4(const TI* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) pack_nchw_v4_kernel(const TI* __restrict__ src, TO* __restrict__ dst,
                                                            int C, int HW) {
   __shared__ __align__(16) float tile[128 * 32];
   const size_t img = blockIdx.z;
   const int hw0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
-  const float* s = src + img * static_cast<size_t>(C) * HW;
+  const TI* s = src + img * static_cast<size_t>(C) * HW;
   TO* d = dst + img * static_cast<size_t>(C) * HW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {
@@ -78,7 +90,7 @@ __global__ void __launch_bounds__(256) pack_nchw_v4_kernel(const float* __restri
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c + k < C && hw < HW) r[k] = __ldg(reinterpret_cast<const float4*>(s + static_cast<size_t>(c + k) * HW + hw));
+      if (c + k < C && hw < HW) r[k] = load4<TI>(s + static_cast<size_t>(c + k) * HW + hw);
     }
     const int q = (warp ^ (lane & 7)) * 4;         // swizzled 16-byte column of channels c..c+3
     float* t = tile + (lane * 4) * 32 + q;
@@ -103,18 +115,22 @@ __global__ void __launch_bounds__(256) pack_nchw_v4_kernel(const float* __restri
 int dispatch_pack(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t images, int C,
                   int H, int W, cudaStream_t stream) {
   const int HW = H * W;
-  if (src_dtype == GD4D_F32 && HW % 4 == 0 && C % 4 == 0 &&
-      (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 &&
-      (dst_dtype == GD4D_F32 || dst_dtype == GD4D_BF16)) {
+  const bool v4_types = (src_dtype == GD4D_F32 && (dst_dtype == GD4D_F32 || dst_dtype == GD4D_BF16)) ||
+                        (src_dtype == GD4D_BF16 && dst_dtype == GD4D_BF16);
+  if (v4_types && HW % 4 == 0 && C % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
     for (int64_t i0 = 0; i0 < images; i0 += 65535) {
       const int64_t cnt = images - i0 < 65535 ? images - i0 : 65535;
       dim3 grid((HW + 127) / 128, (C + 31) / 32, static_cast<unsigned>(cnt));
       const size_t off = static_cast<size_t>(i0) * C * HW;
-      if (dst_dtype == GD4D_F32)
-        pack_nchw_v4_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(src) + off,
-                                                             static_cast<float*>(dst) + off, C, HW);
+      if (src_dtype == GD4D_BF16)
+        pack_nchw_v4_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(src) + off, static_cast<__nv_bfloat16*>(dst) + off, C, HW);
+      else if (dst_dtype == GD4D_F32)
+        pack_nchw_v4_kernel<float, float><<<grid, 256, 0, stream>>>(static_cast<const float*>(src) + off,
+                                                                    static_cast<float*>(dst) + off, C, HW);
       else
-        pack_nchw_v4_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        pack_nchw_v4_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>(
             static_cast<const float*>(src) + off, static_cast<__nv_bfloat16*>(dst) + off, C, HW);
       if (cudaGetLastError() != cudaSuccess) return GD4D_ERR_CUDA;
     }

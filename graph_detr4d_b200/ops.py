@@ -30,8 +30,10 @@ L2_PREFETCH = os.environ.get("GD4D_L2_PREFETCH", "0") != "0"   # prefetch.global
 #           value row read once, one reduction per run (486 k -> ~110 k reductions at N = 6)
 # Measured r2 (profiles/r2_bwd_variants.json, bench layer-0 inputs, us per backward call, sorted vs atomics):
 # fp32 N = 6: 136 vs 141, fp32 N = 12: 232 vs 271, bf16 N = 12: 254 vs 245; inside the graphed training step
-# (tools/ab_step.py, same process): 4.378 vs 4.448 ms at N = 6, 5.284 vs 5.585 ms at N = 12 (fp32).
-# "auto" therefore takes the sorted path for fp32 maps.  GD4D_SORTED_BWD=0 / 1 forces one of them.
+# (tools/ab_step.py, same process, with the forward emitting the records): fp32 4.378 vs 4.448 ms at N = 6, 5.284 vs
+# 5.585 ms at N = 12; bf16 4.312 vs 4.304 ms at N = 6, 5.161 vs 5.277 ms at N = 12.
+# "auto" therefore takes the sorted path for fp32 maps, and for bf16 maps from 12 camera images up.
+# GD4D_SORTED_BWD=0 / 1 forces one of them.
 _SORTED_ENV = os.environ.get("GD4D_SORTED_BWD", "auto")
 SORTED_BACKWARD = {"0": False, "1": True}.get(_SORTED_ENV, "auto")
 _LAUNCHES = 0      # kernels of libgd4d_xview.so launched by this process (bench: gpu_launches)
@@ -77,12 +79,12 @@ def _sched_ptr(device) -> int:
 _BWD_WS = {}
 
 
-def sorted_backward_active(mode: int, wide: bool, value_dtype_code: int) -> bool:
+def sorted_backward_active(mode: int, wide: bool, value_dtype_code: int, cams: int = 0) -> bool:
     """Which backward gd4d_xview_backward will run for this configuration (see SORTED_BACKWARD)."""
     if not (wide and mode == MODE_C):
         return False
     if SORTED_BACKWARD == "auto":
-        return value_dtype_code == F32
+        return value_dtype_code == F32 or cams >= 12
     return bool(SORTED_BACKWARD)
 
 
@@ -90,7 +92,7 @@ def _attach_bwd_ws(p: XViewParams, device) -> int:
     """Scratch of the sorted wide backward, one per (device, stream) like the work counter: its
     counters + row histogram are zeroed once here, every launch leaves them zeroed again.
     Returns the number of kernels the backward call will launch."""
-    if not sorted_backward_active(p.mode, bool(p.wide), p.value_dtype):
+    if not sorted_backward_active(p.mode, bool(p.wide), p.value_dtype, p.B * p.N):
         return 1
     need = int(_lib.load().gd4d_xview_bwd_ws_bytes(C.byref(p)))
     if need < 0:
@@ -126,7 +128,7 @@ _SORT_STREAMS = {}
 
 def _presort(p: XViewParams, device):
     """``p``: parameters filled as for the backward (forward inputs are enough).  -> (scratch, done-event) or None."""
-    if not (PRESORT and sorted_backward_active(p.mode, bool(p.wide), p.value_dtype)):
+    if not (PRESORT and sorted_backward_active(p.mode, bool(p.wide), p.value_dtype, p.B * p.N)):
         return None
     lib = _lib.load()
     need = int(lib.gd4d_xview_bwd_ws_bytes(C.byref(p)))
@@ -156,7 +158,7 @@ def _presort(p: XViewParams, device):
 def _emit_scratch(p: XViewParams, device, needs_grad: bool):
     """Scratch for a forward that emits the sorted backward's records: attaches it to ``p`` (forward params) and
     returns the ``presort`` tuple the backward takes, or None when that path does not apply."""
-    if not (FWD_EMIT and not PRESORT and needs_grad and sorted_backward_active(p.mode, bool(p.wide), p.value_dtype)):
+    if not (FWD_EMIT and not PRESORT and needs_grad and sorted_backward_active(p.mode, bool(p.wide), p.value_dtype, p.B * p.N)):
         return None
     need = int(_lib.load().gd4d_xview_bwd_ws_bytes(C.byref(p)))
     if need < 0:
@@ -284,13 +286,15 @@ class _SinkFn(torch.autograd.Function):
             return (None,) + (None,) * len(ctx.meta)
         outs = []
         for buf, (shape, dtype, nchw) in zip(bufs, ctx.meta):
-            if nchw and dtype == torch.float32:
-                # NCHW producer: one tiled transpose (gd4d_unpack_nhwc) instead of the strided
-                # elementwise copy autograd would make to match the leaf's / conv's layout
-                g = torch.empty(shape, device=buf.device, dtype=torch.float32)
-                st = _lib.load().gd4d_unpack_nhwc(buf.data_ptr(), g.data_ptr(), shape[0] * shape[1], shape[2],
-                                                  shape[3], shape[4], _stream_ptr(buf.device))
-                _lib.check(st, "gd4d_unpack_nhwc")
+            if nchw and dtype in (torch.float32, torch.bfloat16):
+                # NCHW producer: one tiled transpose (gd4d_unpack_nhwc[_cast]) instead of the strided
+                # elementwise copy autograd would make to match the leaf's / conv's layout; a bf16 producer
+                # gets its bf16 gradient from the same launch (no separate 4-byte -> 2-byte pass)
+                g = torch.empty(shape, device=buf.device, dtype=dtype)
+                st = _lib.load().gd4d_unpack_nhwc_cast(buf.data_ptr(), g.data_ptr(), F32 if dtype == torch.float32 else BF16,
+                                                       shape[0] * shape[1], shape[2], shape[3], shape[4],
+                                                       _stream_ptr(buf.device))
+                _lib.check(st, "gd4d_unpack_nhwc_cast")
                 _count()
             else:                                          # channels-last producer: a view, no copy
                 g = buf.permute(0, 3, 1, 2).unflatten(0, shape[:2])

@@ -206,6 +206,11 @@ GD4D_API int gd4d_pack_nchw(const void* src, void* dst, int32_t src_dtype, int32
 GD4D_API int gd4d_unpack_nhwc(const float* src, float* dst, int64_t images, int32_t C, int32_t H,
                      int32_t W, void* cuda_stream);
 
+/* gd4d_unpack_nhwc with the cast folded in: fp32 channel-last gradient map -> NCHW in dst_dtype (gd4d_dtype), for
+ * producers that hold their maps in bf16 (autograd wants the gradient in the leaf's dtype and layout). */
+GD4D_API int gd4d_unpack_nhwc_cast(const float* src, void* dst, int32_t dst_dtype, int64_t images, int32_t C,
+                                   int32_t H, int32_t W, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

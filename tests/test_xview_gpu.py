@@ -373,6 +373,31 @@ def test_pack_kernels_exact_all_paths(C, H_, W_):
     want = f.flatten(0, 1).permute(0, 2, 3, 1).contiguous()
     assert torch.equal(ops.pack_level(f), want)
     assert torch.equal(ops.pack_level(f, torch.bfloat16), want.to(torch.bfloat16))
+    fb = f.to(torch.bfloat16)                                                   # bf16 producer: bf16 -> bf16 paths
+    assert torch.equal(ops.pack_level(fb), fb.flatten(0, 1).permute(0, 2, 3, 1).contiguous())
+
+
+def test_bf16_producer_gets_its_bf16_nchw_gradient_from_one_launch():
+    """bf16 NCHW leaf maps: the shared fp32 channel-last grad map comes back as a bf16 NCHW tensor through
+    gd4d_unpack_nhwc_cast (every level, incl. the ones whose H*W is not a multiple of 4); equal to converting the
+    gradient the fp32-leaf path produces."""
+    sc = H.scene(B=1, T=1, Q=96)
+    logits, offsets, cam = H.rand_inputs_c(sc)
+    cfg = XViewConfig(MODE_C, 8, 4, tuple(syn.PC_RANGE), 900.0, 1600.0, wide=True)
+    g = torch.Generator().manual_seed(9)
+    g1 = torch.randn(1, 8, 96, 256, generator=g).cuda()
+    grads = {}
+    for leaf_dtype in (torch.float32, torch.bfloat16):
+        feats = [_leaf(f.to(torch.bfloat16).to(leaf_dtype).cuda()) for f in sc["feats"]]
+        packed = ops.pack_features(feats, torch.bfloat16)
+        agg, ws = ops.xview_attention(cfg, packed, sc["ref"].cuda(), logits.cuda(), offsets.cuda(), cam.cuda(),
+                                      sc["l2i"].cuda())
+        (agg * g1).sum().backward()
+        grads[leaf_dtype] = [f.grad for f in feats]
+    for a, b in zip(grads[torch.bfloat16], grads[torch.float32]):
+        assert a.dtype == torch.bfloat16 and a.is_contiguous() and a.shape == b.shape
+        # fp32 atomics order differs run to run by ~1e-7: compare after the same rounding, 1 bf16 ulp
+        assert H.rel_err(a.float(), b.to(torch.bfloat16).float()) <= 2 ** -7
 
 
 def test_presorted_backward_on_a_side_stream_matches():
