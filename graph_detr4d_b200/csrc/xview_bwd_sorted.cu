@@ -15,13 +15,16 @@
 // need only the forward's inputs and can run early, on another stream, through gd4d_xview_backward_sort):
 //   K1 emit      warp per (b,q,head): candidates + records exactly as xview_bwd.cu builds them; every
 //                in-map corner takes a slot in its row's histogram (atomicAdd returns its rank) and
-//                writes {row, rank, grad_out row, wt * w_corner} at cid = base + item*4 + corner
+//                writes a 32-byte record {value-row pointer, grad-map offset + level | grad_out row,
+//                wt * w_corner, row, rank} at cid = base + item*4 + corner.  With GD4D_FLAG_FWD_EMIT the
+//                FORWARD kernel writes the same records (xview_fwd.cu) and this launch is skipped.
 //   K2 scan      exclusive prefix over the row histogram (block-local + last-block-done carry scan)
-//   K3 scatter   contribution -> its sorted position row_start[row] + rank
+//   K3 scatter   record -> its sorted position row_start[row] + rank (pure permutation); re-zeroes the
+//                histogram for the next call
 //   K4 owner     warp per 32 consecutive sorted contributions (perfectly balanced; a row that spans
-//                warps is simply reduced by each): value row loaded at run starts only, 4 grad_out
-//                rows in flight, dot -> dots[cid], acc += coef * g, red.add.v4.f32 at run ends;
-//                also re-zeroes the histogram entries it consumed
+//                warps is simply reduced by each): one record per lane, value row fetched at run starts
+//                only (cp.async ring, one batch ahead), 4 grad_out rows in flight, dot -> dots[cid],
+//                acc += coef * g, red.add.v4.f32 at run ends
 //   K5 finish    warp per (b,q,head), ONE LANE PER ITEM: rebuilds the same records, reads its 4 dots
 //                and does what the tail of xview_bwd.cu does (softmax / sigmoid / projection chain)
 // Results equal xview_bwd.cu up to fp32 summation order (tests/test_xview_gpu.py runs both).
