@@ -372,6 +372,7 @@ def measure_decoder(D: Dist, T, dtype, K, W, prewarm_s, keep=False):
         res["live"] = (model, stepper, metas)
     else:
         del stepper, model, host, feats_dev
+        ops.clear_scratch_pool()
         gc.collect()
         torch.cuda.empty_cache()
     return res
@@ -399,6 +400,8 @@ def main():
     if D.rank == 0 and not args.no_roofline:
         roof, roof_fwd = kernel_roofline(model, stepper.static_feats, metas, T, dtype, D.dev)
     del stepper, model
+    from graph_detr4d_b200 import ops as _ops
+    _ops.clear_scratch_pool()
     gc.collect()
     torch.cuda.empty_cache()
 

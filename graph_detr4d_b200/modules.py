@@ -230,6 +230,8 @@ def clear_pack_cache():
 
 
 def clear_caches():
+    from . import ops as _ops
+    _ops.clear_scratch_pool()
     _PACK_CACHE.clear()
     _L2I_CACHE.__init__()
     _L2I_CACHE.static = False

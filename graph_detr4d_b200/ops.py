@@ -119,6 +119,7 @@ def _attach_bwd_ws(p: XViewParams, device) -> int:
 # Measured r2 (tools/ab_step.py, same process): 4.599 vs 4.579 ms at N = 6, 5.292 vs 5.303 ms at N = 12 -- no gain:
 # the 900-CTA emit kernel does not hide under the layer's GEMMs, it competes with them for the same SMs.  Off.
 PRESORT = os.environ.get("GD4D_PRESORT", "0") != "0"
+_SCRATCH_FREE = {}
 # Sorted backward: let the FORWARD kernel emit the contribution records (GD4D_FLAG_FWD_EMIT: it builds the same
 # per-item records anyway), so the backward call starts at the scan.  Scratch per (forward, backward) pair, owned by
 # the autograd node, same stream throughout.  GD4D_FWD_EMIT=0 keeps the emit kernel in the backward.
@@ -164,12 +165,47 @@ def _emit_scratch(p: XViewParams, device, needs_grad: bool):
     if need < 0:
         return None
     rows = sum(p.B * p.N * p.level_h[l] * p.level_w[l] for l in range(p.L))
-    with torch.no_grad():
-        ws = torch.empty(need, dtype=torch.uint8, device=device)
-        ws[:256 + (4 * rows + 255) // 256 * 256].zero_()
+    # a backward leaves its scratch clean (histogram and counters zero again), so scratches go back to a free list
+    # when their backward has been launched and are handed out again without a memset; one whose backward never
+    # ran is simply dropped.  Under CUDA-graph capture the warm-up steps have filled the list: no allocation and no
+    # memset node inside the graph.
+    key = (torch.device(device).index, need, rows)
+    free = _SCRATCH_FREE.setdefault(key, [])
+    if free:
+        ws = free.pop()
+        ev, stream_ptr = ws._gd4d_last
+        if stream_ptr != _stream_ptr(device) and not torch.cuda.is_current_stream_capturing():
+            if ev is not None:
+                torch.cuda.current_stream(device).wait_event(ev)   # last used on another stream
+    else:
+        with torch.no_grad():
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+            ws[:256 + (4 * rows + 255) // 256 * 256].zero_()
+        ws._gd4d_key = key
     p.bwd_ws, p.bwd_ws_bytes = ws.data_ptr(), ws.numel()
     p.flags |= _lib.FLAG_FWD_EMIT
     return ws, None
+
+
+def _recycle_scratch(presort):
+    """After the backward has been launched (stream order keeps later users behind it): a forward-emit scratch is
+    clean again and reusable.  Side-stream (presort) scratches are not pooled (their first use is on another stream)."""
+    if presort is not None and presort[1] is None:
+        key = getattr(presort[0], "_gd4d_key", None)
+        if key is not None and len(_SCRATCH_FREE.setdefault(key, [])) < 64:
+            ws = presort[0]
+            if torch.cuda.is_current_stream_capturing():           # static inside a graph: same order every replay
+                ws._gd4d_last = (None, _stream_ptr(ws.device))
+            else:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(ws.device))
+                ws._gd4d_last = (ev, _stream_ptr(ws.device))
+            _SCRATCH_FREE[key].append(ws)
+
+
+def clear_scratch_pool():
+    """Drop the pooled forward-emit scratches (188 MB each at N = 6)."""
+    _SCRATCH_FREE.clear()
 
 
 def _use_presorted(p: XViewParams, presort, device) -> int:
@@ -179,7 +215,7 @@ def _use_presorted(p: XViewParams, presort, device) -> int:
     p.bwd_ws, p.bwd_ws_bytes = ws.data_ptr(), ws.numel()
     if done is None:
         p.flags |= _lib.FLAG_BWD_EMITTED
-        return 4
+        return 4                                            # (the caller returns ws to the free list after the launch)
     torch.cuda.current_stream(device).wait_event(done)
     p.flags |= _lib.FLAG_BWD_PRESORTED
     return 2
@@ -529,6 +565,7 @@ def xview_backward(cfg: XViewConfig, values: Sequence[torch.Tensor], B: int, N: 
     st = _lib.load().gd4d_xview_backward(C.byref(p), _stream_ptr(ref.device))
     _lib.check(st, "gd4d_xview_backward")
     _count(n_launch)
+    _recycle_scratch(presort)
     return g_attn, g_off, g_cam, g_ref
 
 
@@ -662,6 +699,7 @@ def xview_backward_gen(cfg: XViewConfig, values, B: int, N: int, ref, gen, layou
     n_launch = _use_presorted(p, presort, ref.device) if presort is not None else _attach_bwd_ws(p, ref.device)
     _lib.check(_lib.load().gd4d_xview_backward(C.byref(p), _stream_ptr(ref.device)), "gd4d_xview_backward")
     _count(n_launch)
+    _recycle_scratch(presort)
     return g_gen, g_ref
 
 
