@@ -159,8 +159,8 @@ def load(build_if_missing: bool = True):
                 ("gd4d_inverse_sigmoid_bwd", [vp, vp, vp, i64, f32, i32, vp]),
                 ("gd4d_ref_update", [vp, i32, vp, vp, i64, f32, vp]),
                 ("gd4d_bias_act", [vp, vp, i64, i32, i32, vp]),
-                ("gd4d_add_layernorm_fwd", [vp] * 12 + [i64, i32, f32, i32, vp]),
-                ("gd4d_add_layernorm_bwd", [vp] * 9 + [i64, i32, i32, vp]),
+                ("gd4d_add_layernorm_fwd", [vp] * 14 + [i64, i32, f32, i32, vp]),
+                ("gd4d_add_layernorm_bwd", [vp] * 11 + [i64, i32, i32, vp]),
                 ("gd4d_adamw_chunk", []),
                 ("gd4d_adamw_multi", [vp, vp, i32, vp, f32, f32, f32, f32, f32, vp]),
                 ("gd4d_softmax_bwd", [vp, vp, vp, i64, i32, vp]),

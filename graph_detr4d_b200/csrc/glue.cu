@@ -88,6 +88,7 @@ add_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
                          const float* __restrict__ gamma,
                          const float* __restrict__ beta, const float* __restrict__ pos,
                          float* __restrict__ y, float* __restrict__ y2,
+                         float* __restrict__ yc1, float* __restrict__ yc2,
                          float* __restrict__ s_out, float* __restrict__ mean_out,
                          float* __restrict__ rstd_out, int64_t rows, float eps, bool relu) {
   constexpr int C = NV * 128;
@@ -137,6 +138,10 @@ add_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
     o.w = (v[j].w - mean) * rstd * g.w + b.w;
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     *reinterpret_cast<float4*>(y + base + c) = o;
+    // identical copies of y for further consumers: each autograd consumer then hands back its own gradient and
+    // the backward kernel sums them in registers, instead of one elementwise add launch per extra consumer
+    if (yc1 != nullptr) *reinterpret_cast<float4*>(yc1 + base + c) = o;
+    if (yc2 != nullptr) *reinterpret_cast<float4*>(yc2 + base + c) = o;
     if (y2 != nullptr) {  // second output y + pos: the next block's "query + query_pos"
       const float4 q = *reinterpret_cast<const float4*>(pos + base + c);
       o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
@@ -148,6 +153,7 @@ add_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
 template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32)
 add_layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2,
+                         const float* __restrict__ gc1, const float* __restrict__ gc2,
                          const float* __restrict__ s,
                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                          const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -165,9 +171,18 @@ add_layernorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__
   for (int j = 0; j < NV; ++j) {
     const int c = (j * 32 + lane) * 4;
     const float4 sv = *reinterpret_cast<const float4*>(s + base + c);
-    float4 g = *reinterpret_cast<const float4*>(gy + base + c);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy != nullptr) g = *reinterpret_cast<const float4*>(gy + base + c);
     if (gy2 != nullptr) {  // gradient of the second output (y + pos)
       const float4 h = *reinterpret_cast<const float4*>(gy2 + base + c);
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    }
+    if (gc1 != nullptr) {  // gradients of the copies of y
+      const float4 h = *reinterpret_cast<const float4*>(gc1 + base + c);
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    }
+    if (gc2 != nullptr) {
+      const float4 h = *reinterpret_cast<const float4*>(gc2 + base + c);
       g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
     }
     const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -284,8 +299,9 @@ int gd4d_bias_act(float* y, const float* bias, int64_t rows, int32_t C, int32_t 
 
 int gd4d_add_layernorm_fwd(const float* x, const float* xbias, const float* r1, const float* r2,
                            const float* gamma, const float* beta, const float* pos, float* y,
-                           float* y2, float* s_out, float* mean, float* rstd, int64_t rows,
-                           int32_t C, float eps, int32_t relu, void* cuda_stream) {
+                           float* y2, float* y_copy1, float* y_copy2, float* s_out, float* mean, float* rstd,
+                           int64_t rows, int32_t C, float eps, int32_t relu, void* cuda_stream) {
+  if (!gd4d::al16(y_copy1) || !gd4d::al16(y_copy2)) return GD4D_ERR_ALIGN;
   if ((pos == nullptr) != (y2 == nullptr)) return GD4D_ERR_NULL;
   if (!gd4d::al16(pos) || !gd4d::al16(y2)) return GD4D_ERR_ALIGN;
   if (x == nullptr || gamma == nullptr || beta == nullptr || y == nullptr || mean == nullptr ||
@@ -302,8 +318,8 @@ int gd4d_add_layernorm_fwd(const float* x, const float* xbias, const float* r1, 
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
 #define GD4D_LN_FWD(NV)                                                                          \
   gd4d::add_layernorm_fwd_kernel<NV><<<grid, block, 0, st>>>(x, xbias, r1, r2, gamma, beta, pos, y, \
-                                                             y2, s_out, mean, rstd, rows, eps,       \
-                                                             relu != 0)
+                                                             y2, y_copy1, y_copy2, s_out, mean, rstd, \
+                                                             rows, eps, relu != 0)
   switch (C / 128) {
     case 1: GD4D_LN_FWD(1); break;
     case 2: GD4D_LN_FWD(2); break;
@@ -318,13 +334,14 @@ int gd4d_add_layernorm_fwd(const float* x, const float* xbias, const float* r1, 
   return gd4d::launched();
 }
 
-int gd4d_add_layernorm_bwd(const float* gy, const float* gy2, const float* s, const float* mean,
-                           const float* rstd,
+int gd4d_add_layernorm_bwd(const float* gy, const float* gy2, const float* g_copy1, const float* g_copy2,
+                           const float* s, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, float* gs, float* g_masked,
                            int64_t rows, int32_t C, int32_t relu, void* cuda_stream) {
-  if (gy == nullptr || s == nullptr || mean == nullptr || rstd == nullptr || gamma == nullptr ||
-      gs == nullptr || (relu && beta == nullptr))
+  if ((gy == nullptr && gy2 == nullptr && g_copy1 == nullptr && g_copy2 == nullptr) || s == nullptr ||
+      mean == nullptr || rstd == nullptr || gamma == nullptr || gs == nullptr || (relu && beta == nullptr))
     return GD4D_ERR_NULL;
+  if (!gd4d::al16(g_copy1) || !gd4d::al16(g_copy2)) return GD4D_ERR_ALIGN;
   if (rows <= 0 || rows > (1LL << 31) || C <= 0 || C % 128 != 0 || C > 1024) return GD4D_ERR_DIMS;
   if (!gd4d::al16(gy) || !gd4d::al16(gy2) || !gd4d::al16(s) || !gd4d::al16(gamma) || !gd4d::al16(beta) ||
       !gd4d::al16(gs) || !gd4d::al16(g_masked))
@@ -333,8 +350,8 @@ int gd4d_add_layernorm_bwd(const float* gy, const float* gy2, const float* s, co
   const int block = gd4d::kLnWarps * 32;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
 #define GD4D_LN_BWD(NV)                                                                          \
-  gd4d::add_layernorm_bwd_kernel<NV><<<grid, block, 0, st>>>(gy, gy2, s, mean, rstd, gamma, beta, \
-                                                             gs, g_masked, rows, relu != 0)
+  gd4d::add_layernorm_bwd_kernel<NV><<<grid, block, 0, st>>>(gy, gy2, g_copy1, g_copy2, s, mean, rstd, gamma, \
+                                                             beta, gs, g_masked, rows, relu != 0)
   switch (C / 128) {
     case 1: GD4D_LN_BWD(1); break;
     case 2: GD4D_LN_BWD(2); break;

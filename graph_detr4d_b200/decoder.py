@@ -121,9 +121,12 @@ class DecoderLayer(nn.Module):
         self.ffns = nn.ModuleList([FFN(embed_dims, feedforward_channels, dropout)])
         self.norms = nn.ModuleList([nn.LayerNorm(embed_dims) for _ in range(3)])
 
-    def forward(self, query, value, query_pos, reference_points, img_metas, q_plus_pos=None, want_next=False):
+    def forward(self, query, value, query_pos, reference_points, img_metas, q_plus_pos=None, want_next=False,
+                query_res=None):
         """``q_plus_pos``: ``query + query_pos`` if the previous layer already produced it;
-        ``want_next``: also return ``output + query_pos`` for the next layer -> (output, output + pos)."""
+        ``want_next``: also return what the NEXT layer consumes -> (output, output + pos, output copy for the next
+        layer's value projection, output copy for its residual); ``query_res``: the copy of ``query`` to use as this
+        layer's first residual (each consumer of a fused LayerNorm's result gets its own copy, fused.add_layernorm)."""
         # post-norm layer: every "branch + identity" sum is folded into the LayerNorm that
         # follows it (fused.add_layernorm: one launch) when the tensors are CUDA fp32
         fuse = all(fused.can_fuse_layernorm(query, n) for n in self.norms)
@@ -134,18 +137,29 @@ class DecoderLayer(nn.Module):
                           reference_points=reference_points, img_metas=img_metas)
             query = fast_layer_norm(query, self.norms[1])
             out = fast_layer_norm(self.ffns[0](query), self.norms[2])
-            return (out, None) if want_next else out
+            return (out, None, out, out) if want_next else out
         # every LayerNorm whose output feeds an attention block also emits output + query_pos
         out, bias = self.attentions[0].branch(query, query_pos, defer_bias=True, qk_in=q_plus_pos)
-        query, qp = fused.add_layernorm(out, self.norms[0], query, xbias=bias, pos=query_pos)
+        query, qp = fused.add_layernorm(out, self.norms[0], query if query_res is None else query_res, xbias=bias,
+                                        pos=query_pos)
         out, res, pos, bias = cross.forward_parts(query, None, value, None, query_pos=query_pos,
                                                   reference_points=reference_points, img_metas=img_metas,
                                                   defer_bias=True, query_with_pos=qp)
-        query = fused.add_layernorm(out, self.norms[1], res, pos, xbias=bias)
+        # two consumers (the FFN's first Linear, the next residual): one copy each, their gradients meet again
+        # inside the LayerNorm backward kernel instead of in an elementwise add
+        if not fused.LN_COPIES:                            # one output, autograd adds the consumers' gradients
+            query = fused.add_layernorm(out, self.norms[1], res, pos, xbias=bias)
+            out, bias = self.ffns[0].branch(query, defer_bias=True)
+            if want_next:
+                o, qp_next = fused.add_layernorm(out, self.norms[2], query, xbias=bias, pos=query_pos)
+                return o, qp_next, o, o
+            return fused.add_layernorm(out, self.norms[2], query, xbias=bias)
+        query, query_r = fused.add_layernorm(out, self.norms[1], res, pos, xbias=bias, copies=1)
         out, bias = self.ffns[0].branch(query, defer_bias=True)
-        if want_next:
-            return fused.add_layernorm(out, self.norms[2], query, xbias=bias, pos=query_pos)
-        return fused.add_layernorm(out, self.norms[2], query, xbias=bias)
+        if want_next:   # consumers: the stacked output, the next layer's value projection and its first residual
+            o, qp_next, o_v, o_r = fused.add_layernorm(out, self.norms[2], query_r, xbias=bias, pos=query_pos, copies=2)
+            return o, qp_next, o_v, o_r
+        return fused.add_layernorm(out, self.norms[2], query_r, xbias=bias)
 
 
 class Detr3DTransformerDecoder(nn.Module):
@@ -187,12 +201,14 @@ class Detr3DTransformerDecoder(nn.Module):
         intermediate, intermediate_ref = [], []
         self._refresh_generator_packs(query)
         q_plus_pos = None
+        out_v = out_r = output                     # what the next layer's value projection / first residual consume
         for lid, layer in enumerate(self.layers):
             if lid + 1 < len(self.layers):
-                output, q_plus_pos = layer(output, value, query_pos, reference_points, img_metas,
-                                           q_plus_pos=q_plus_pos, want_next=True)
+                output, q_plus_pos, out_v, out_r = layer(out_v, value, query_pos, reference_points, img_metas,
+                                                         q_plus_pos=q_plus_pos, want_next=True, query_res=out_r)
             else:
-                output = layer(output, value, query_pos, reference_points, img_metas, q_plus_pos=q_plus_pos)
+                output = layer(out_v, value, query_pos, reference_points, img_metas, q_plus_pos=q_plus_pos,
+                               query_res=out_r)
             if reg_branches is not None:                                    # :201-214
                 tmp = output.permute(1, 0, 2)
                 tmp = _run_branch(reg_branches[lid], tmp)

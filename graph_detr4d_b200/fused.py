@@ -112,6 +112,7 @@ def softmax_bwd_(grad: torch.Tensor, probs: torch.Tensor) -> torch.Tensor:
 
 
 SOFTMAX_BWD = True     # A/B switch (tools/ab_step.py)
+LN_COPIES = True       # A/B switch: one output copy per consumer of a fused LayerNorm result (decoder.DecoderLayer)
 
 
 def can_fuse_softmax_bwd(grad: torch.Tensor, probs: torch.Tensor) -> bool:
@@ -127,7 +128,7 @@ class _AddLayerNormFn(torch.autograd.Function):
     with ``add_bias=False``)."""
 
     @staticmethod
-    def forward(ctx, x, r1, r2, gamma, beta, eps: float, relu: bool, owner, xbias=None, pos=None):
+    def forward(ctx, x, r1, r2, gamma, beta, eps: float, relu: bool, owner, xbias=None, pos=None, copies: int = 0):
         C = x.shape[-1]
         xc = _f32c(x, "x")
         r1c = _f32c(r1, "residual") if r1 is not None else None
@@ -141,40 +142,48 @@ class _AddLayerNormFn(torch.autograd.Function):
         if posc is not None and posc.shape != xc.shape:
             raise ValueError(f"add_layernorm: pos {tuple(posc.shape)} vs x {tuple(xc.shape)}")
         y2 = torch.empty_like(xc) if posc is not None else None
+        if not 0 <= copies <= 2:
+            raise ValueError("add_layernorm: at most 2 extra copies of the output")
+        ycs = [torch.empty_like(xc) for _ in range(copies)]
         need_s = r1c is not None or xbias is not None
         s = torch.empty_like(xc) if need_s else xc
         stats = torch.empty(2, rows, device=xc.device, dtype=torch.float32)
         st = _lib.load().gd4d_add_layernorm_fwd(
             xc.data_ptr(), _ptr(xbias), _ptr(r1c), _ptr(r2c), gamma.data_ptr(), beta.data_ptr(), _ptr(posc),
-            y.data_ptr(), _ptr(y2), s.data_ptr() if need_s else None, stats[0].data_ptr(), stats[1].data_ptr(),
+            y.data_ptr(), _ptr(y2), ycs[0].data_ptr() if copies > 0 else None, ycs[1].data_ptr() if copies > 1 else None,
+            s.data_ptr() if need_s else None, stats[0].data_ptr(), stats[1].data_ptr(),
             rows, C, eps, int(relu), _stream_ptr(xc.device))
         _lib.check(st, "gd4d_add_layernorm_fwd")
         _count()
         ctx.save_for_backward(s, stats, gamma, beta)
         ctx.relu, ctx.owner = relu, owner
         ctx.has = (r1 is not None, r2 is not None)
+        ctx.has_y2 = y2 is not None
         ctx.set_materialize_grads(False)                   # an unused output's gradient arrives as None
-        if y2 is not None:
-            return y, y2
-        return y
+        outs = (y,) + ((y2,) if y2 is not None else ()) + tuple(ycs)
+        return outs if len(outs) > 1 else y
 
     @staticmethod
-    def backward(ctx, gy, gy2=None):
+    def backward(ctx, gy, *rest):
         s, stats, gamma, beta = ctx.saved_tensors
         C = s.shape[-1]
         rows = s.numel() // C
+        rest = list(rest)
+        gy2 = rest.pop(0) if ctx.has_y2 else None
+        gcs = rest + [None] * (2 - len(rest))              # gradients of the copies of y
         g_pos = gy2                                        # d(y + pos)/dpos = 1
-        if gy is None:
-            gy, gy2 = gy2, None
-        if gy is None:
-            return (None,) * 10
-        gy = _f32c(gy, "grad")
+        if gy is None and gy2 is None and gcs[0] is None and gcs[1] is None:
+            return (None,) * 11
+        gy = _f32c(gy, "grad") if gy is not None else None
         gy2 = _f32c(gy2, "grad2") if gy2 is not None else None
+        gcs = [_f32c(g, "grad copy") if g is not None else None for g in gcs]
+        n_in = sum(g is not None for g in (gy, gy2, *gcs))
         gs = torch.empty_like(s)
         need_wgrad = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
-        gm = torch.empty_like(s) if ((ctx.relu or gy2 is not None) and need_wgrad) else None
+        gm = torch.empty_like(s) if ((ctx.relu or n_in > 1 or gy is None) and need_wgrad) else None
         st = _lib.load().gd4d_add_layernorm_bwd(
-            gy.data_ptr(), _ptr(gy2), s.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), gamma.data_ptr(),
+            _ptr(gy), _ptr(gy2), _ptr(gcs[0]), _ptr(gcs[1]), s.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+            gamma.data_ptr(),
             beta.data_ptr(), gs.data_ptr(), _ptr(gm), rows, C, int(ctx.relu), _stream_ptr(s.device))
         _lib.check(st, "gd4d_add_layernorm_bwd")
         _count()
@@ -190,21 +199,24 @@ class _AddLayerNormFn(torch.autograd.Function):
                 dgamma = (G * ((X - mean) * rstd)).sum(0)
                 dbeta = G.sum(0)
         return (gs, gs if ctx.has[0] else None, gs if ctx.has[1] else None, dgamma, dbeta, None, None, None,
-                None, g_pos)
+                None, g_pos, None)
 
 
 def add_layernorm(x: torch.Tensor, ln: torch.nn.LayerNorm, r1: Optional[torch.Tensor] = None,
                   r2: Optional[torch.Tensor] = None, relu: bool = False,
-                  xbias: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None):
+                  xbias: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None, copies: int = 0):
     """[relu](ln(x + xbias + r1 + r2)) in one launch (forward) / one launch (backward dX).
     ``xbias``: the (C,) bias of the Linear that produced ``x`` with ``add_bias=False``.
-    ``pos``: also return ``y + pos`` (the next attention block's query + query_pos) -> (y, y + pos)."""
+    ``pos``: also return ``y + pos`` (the next attention block's query + query_pos) -> (y, y + pos).
+    ``copies`` (0..2): also return that many identical copies of ``y`` (after ``y + pos`` if requested), ONE PER
+    FURTHER CONSUMER of the result: every consumer then sends its own gradient back and the backward kernel sums
+    them in registers; with a single output autograd would launch an elementwise add per extra consumer."""
     if r1 is None and r2 is not None:
         r1, r2 = r2, None
     owner = (ln.weight, ln.bias) if ln.weight.requires_grad else None
     if xbias is not None:
         xbias = _f32c(xbias.detach(), "xbias")
-    return _AddLayerNormFn.apply(x, r1, r2, ln.weight, ln.bias, float(ln.eps), bool(relu), owner, xbias, pos)
+    return _AddLayerNormFn.apply(x, r1, r2, ln.weight, ln.bias, float(ln.eps), bool(relu), owner, xbias, pos, int(copies))
 
 
 def can_fuse_layernorm(x: torch.Tensor, ln: torch.nn.LayerNorm) -> bool:

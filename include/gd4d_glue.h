@@ -55,16 +55,22 @@ GD4D_API int gd4d_bias_act(float* y, const float* bias, int64_t rows, int32_t C,
  * both or neither: the "query + query_pos" the next attention block starts with).
  * Writes y (rows,C), mean/rstd (rows) and s (s_out is required whenever s != x).
  * C must be a multiple of 128 and <= 1024; all row pointers 16-byte aligned. */
+/* y_copy1 / y_copy2 (optional): identical copies of y, one per further autograd consumer of the result (the FFN
+ * input and the next residual; the next layer's value input, its residual and the stacked output): each consumer
+ * hands back its own gradient and gd4d_add_layernorm_bwd sums them in registers -- autograd would otherwise launch
+ * one elementwise add per extra consumer (3 per decoder layer). */
 GD4D_API int gd4d_add_layernorm_fwd(const float* x, const float* xbias, const float* r1,
                                     const float* r2, const float* gamma, const float* beta,
-                                    const float* pos, float* y, float* y2, float* s_out,
-                                    float* mean, float* rstd, int64_t rows, int32_t C, float eps,
+                                    const float* pos, float* y, float* y2, float* y_copy1, float* y_copy2,
+                                    float* s_out, float* mean, float* rstd, int64_t rows, int32_t C, float eps,
                                     int32_t relu, void* cuda_stream);
-/* gs = dL/ds for the incoming gradient gy (+ gy2, the gradient of y2, optional); the same gs
+/* gs = dL/ds for the incoming gradients gy, gy2 (of y2), g_copy1, g_copy2 (of the copies) -- any may be NULL, at
+ * least one is not; the same gs
  * flows to x, r1 and r2.  With relu the incoming gradient is first masked by [y > 0] (recomputed
  * from s, mean, rstd, gamma, beta).  If g_masked != NULL the effective incoming gradient
  * (summed and/or masked) is written out for the deferred gamma/beta reduction. */
-GD4D_API int gd4d_add_layernorm_bwd(const float* gy, const float* gy2, const float* s,
+GD4D_API int gd4d_add_layernorm_bwd(const float* gy, const float* gy2, const float* g_copy1,
+                                    const float* g_copy2, const float* s,
                                     const float* mean, const float* rstd, const float* gamma,
                                     const float* beta, float* gs, float* g_masked, int64_t rows,
                                     int32_t C, int32_t relu, void* cuda_stream);

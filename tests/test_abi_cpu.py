@@ -75,13 +75,15 @@ def test_launch_info_and_status_codes():
     assert lib.gd4d_inverse_sigmoid_bwd(0x1000, 0x1000, 0x1000, 0, 1e-5, 0, None) == -2
     assert lib.gd4d_ref_update(0x1000, 4, 0x1000, 0x1000, 10, 1e-5, None) == -2      # reg_stride < 5
     a = 0x1000
-    ln = lib.gd4d_add_layernorm_fwd          # x, xbias, r1, r2, gamma, beta, pos, y, y2, s_out, mean, rstd, ...
-    assert ln(a, None, None, None, a, a, None, a, None, None, a, a, 900, 200, 1e-5, 0, None) == -2
-    assert ln(a + 4, None, None, None, a, a, None, a, None, None, a, a, 900, 256, 1e-5, 0, None) == -4
-    assert ln(a, a, None, None, a, a, None, a, None, None, a, a, 900, 256, 1e-5, 0, None) == -1    # s_out
-    assert ln(a, None, None, None, a, a, a, a, None, None, a, a, 900, 256, 1e-5, 0, None) == -1    # pos w/o y2
+    ln = lib.gd4d_add_layernorm_fwd          # x, xbias, r1, r2, gamma, beta, pos, y, y2, y_copy1, y_copy2, s_out, mean, rstd, ...
+    assert ln(a, None, None, None, a, a, None, a, None, None, None, None, a, a, 900, 200, 1e-5, 0, None) == -2
+    assert ln(a + 4, None, None, None, a, a, None, a, None, None, None, None, a, a, 900, 256, 1e-5, 0, None) == -4
+    assert ln(a, a, None, None, a, a, None, a, None, None, None, None, a, a, 900, 256, 1e-5, 0, None) == -1    # s_out
+    assert ln(a, None, None, None, a, a, a, a, None, None, None, None, a, a, 900, 256, 1e-5, 0, None) == -1    # pos w/o y2
+    assert ln(a, None, None, None, a, a, None, a, None, a + 4, None, None, a, a, 900, 256, 1e-5, 0, None) == -4  # copy alignment
     assert lib.gd4d_bias_act(a, a, 900, 10, 1, None) == -2                                      # C % 4
-    assert lib.gd4d_add_layernorm_bwd(a, None, a, a, a, a, None, a, None, 900, 256, 1, None) == -1   # relu needs beta
+    assert lib.gd4d_add_layernorm_bwd(a, None, None, None, a, a, a, a, None, a, None, 900, 256, 1, None) == -1   # relu needs beta
+    assert lib.gd4d_add_layernorm_bwd(None, None, None, None, a, a, a, a, a, a, None, 900, 256, 0, None) == -1   # no gradient at all
     assert lib.gd4d_unpack_nhwc(a, None, 1, 1, 1, 1, None) == -1
     assert lib.gd4d_match_cost(a, a, a, a, a, 900, 10, 7, 5, 9, 2.0, 0.25, 0.25, 1e-12, None) == -2   # code < 8
     pc = (C.c_float * 6)(*[0.0] * 6)

@@ -266,3 +266,36 @@ def test_one_pass_softmax_backward_matches_aten(rows, cols):
     got = fused.softmax_bwd_(go.clone(), p)
     assert _rel(got, want.cpu()) <= 2e-6
     assert not fused.can_fuse_softmax_bwd(go[:, :cols - 1], p[:, :cols - 1])     # ragged / strided: ATen path
+
+
+@pytest.mark.parametrize("with_pos,copies,used", [(False, 1, (True, True)), (True, 2, (True, True, True, True)),
+                                                  (True, 2, (False, True, False, True)), (False, 2, (False, False, True))])
+def test_add_layernorm_output_copies_sum_their_gradients_in_the_kernel(with_pos, copies, used):
+    """``copies``: every consumer of a fused LayerNorm result gets its own identical output; whichever subset of the
+    outputs receives a gradient, dX / dgamma / dbeta equal those of ONE output consumed by all of them."""
+    g = torch.Generator().manual_seed(11)
+    x, r, pos = (torch.randn(50, 2, 256, generator=g) for _ in range(3))
+    ln = torch.nn.LayerNorm(256)
+    with torch.no_grad():
+        ln.weight.add_(torch.randn(256, generator=g) * 0.1)
+        ln.bias.add_(torch.randn(256, generator=g) * 0.1)
+    n_out = 1 + int(with_pos) + copies
+    gys = [torch.randn(50, 2, 256, generator=g) for _ in range(n_out)]
+    # reference: plain torch, one y consumed by everything
+    xr, rr, pr = (t.clone().requires_grad_(True) for t in (x, r, pos))
+    y = torch.nn.functional.layer_norm(xr + rr, (256,), ln.weight, ln.bias, ln.eps)
+    outs_ref = [y] + ([y + pr] if with_pos else []) + [y] * copies
+    sum((o * gy).sum() for o, gy, u in zip(outs_ref, gys, used) if u).backward()
+    want = (xr.grad, rr.grad, ln.weight.grad.clone(), ln.bias.grad.clone())
+    ln.zero_grad()
+    lng = ln.cuda()
+    xg, rg, pg = (t.cuda().requires_grad_(True) for t in (x, r, pos))
+    outs = fused.add_layernorm(xg, lng, rg, pos=pg if with_pos else None, copies=copies)
+    assert len(outs) == n_out
+    for o in outs[1 + int(with_pos):]:
+        assert torch.equal(o, outs[0]) and o.data_ptr() != outs[0].data_ptr()
+    sum((o * gy.cuda()).sum() for o, gy, u in zip(outs, gys, used) if u).backward()
+    for a, b in zip((xg.grad, rg.grad, lng.weight.grad, lng.bias.grad), want):
+        assert _rel(a, b) <= 2e-5
+    if with_pos and used[1]:
+        assert _rel(pg.grad, pr.grad) <= 1e-6

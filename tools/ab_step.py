@@ -25,12 +25,14 @@ def build(name):
     ops.SORTED_BACKWARD = {"sorted": True, "atomics": False}.get(name, "auto")
     ops.PRESORT = name == "presort"
     ops.FWD_EMIT = name != "no_fwd_emit"
+    fused.LN_COPIES = name != "no_copies"
     model = copy.deepcopy(base_model)
     st = GraphedTrainStep(model, lambda f: bench.loss_fn(*(lambda s, _, r: (s, r))(*model(f, metas, 1))), feats, metas)
     fused.ENABLED, modules._PACKED_GEN, graphed.MULTI_TENSOR_ADAMW, fused.SOFTMAX_BWD = True, True, True, True
     ops.SORTED_BACKWARD = "auto"
     ops.PRESORT = False
     ops.FWD_EMIT = True
+    fused.LN_COPIES = True
     return st
 
 
